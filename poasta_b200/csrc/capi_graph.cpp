@@ -1,0 +1,114 @@
+// C ABI: POAGraph handle + readers/writers (include/poasta_b200.h, host-only half).
+// Reference interfaces replaced: graphs/poa.rs:96-382, io/fasta.rs:69, io/graph.rs:24-103,245-502.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "graph_handle.hpp"
+
+using namespace poasta;
+
+static int map_graph_error(GraphError e) {
+    switch (e) {
+        case GraphError::Ok: return POASTA_OK;
+        case GraphError::WeightsUnequalSize: return POASTA_ERR_WEIGHTS_UNEQUAL;
+        case GraphError::InvalidAlignment: return POASTA_ERR_INVALID_ALIGNMENT;
+        case GraphError::Cycle: return POASTA_ERR_GRAPH_CYCLE;
+    }
+    return POASTA_ERR_INVALID_ARG;
+}
+
+static int emit(const std::string &buf, char **out, size_t *len) {
+    char *p = (char *)malloc(buf.size() + 1);
+    if (!p) return POASTA_ERR_IO;
+    memcpy(p, buf.data(), buf.size());
+    p[buf.size()] = 0;
+    *out = p;
+    *len = buf.size();
+    return POASTA_OK;
+}
+
+extern "C" {
+
+poasta_graph *poasta_graph_new(void) { return new (std::nothrow) poasta_graph(); }
+void poasta_graph_free(poasta_graph *g) { delete g; }
+uint32_t poasta_graph_node_count(const poasta_graph *g) { return g->g.node_count(); }
+uint32_t poasta_graph_node_count_with_start_and_end(const poasta_graph *g) { return g->g.node_count_with_start_and_end(); }
+uint32_t poasta_graph_edge_count(const poasta_graph *g) { return g->g.edge_count(); }
+uint32_t poasta_graph_num_sequences(const poasta_graph *g) { return (uint32_t)g->g.sequences.size(); }
+
+int poasta_graph_add_alignment(poasta_graph *h, const char *name, const uint8_t *seq, uint32_t len, const uint32_t *rpos,
+                               const uint32_t *qpos, uint32_t n_pairs, const uint64_t *weights) {
+    if (!h || !name || (len && !seq)) return POASTA_ERR_INVALID_ARG;
+    h->flat_valid = false;
+    if (!rpos || !qpos) return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, nullptr, 0, weights));
+    std::vector<AlignedPair> aln(n_pairs);
+    for (uint32_t i = 0; i < n_pairs; ++i) aln[i] = {rpos[i], qpos[i]};
+    return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, aln.data(), n_pairs, weights));
+}
+
+int poasta_graph_get_view(poasta_graph *h, poasta_graph_view *view) {
+    if (!h || !view) return POASTA_ERR_INVALID_ARG;
+    if (h->g.topological_sorted.size() != h->g.nodes.size()) {
+        GraphError e = h->g.post_process();  // a fresh graph has never been post-processed
+        if (e != GraphError::Ok) return map_graph_error(e);
+        h->flat_valid = false;
+    }
+    *view = h->flat_view();
+    return POASTA_OK;
+}
+
+uint32_t poasta_graph_aligned_nodes(const poasta_graph *h, uint32_t node, uint32_t *out, uint32_t cap) {
+    if (!h || node >= h->g.nodes.size()) return 0;
+    const auto &a = h->g.nodes[node].aligned_nodes;
+    for (uint32_t i = 0; i < a.size() && i < cap; ++i) out[i] = a[i];
+    return (uint32_t)a.size();
+}
+
+int poasta_graph_to_fasta(const poasta_graph *h, char **out, size_t *len) {
+    std::string buf;
+    if (!graph_to_fasta(h->g, buf)) return POASTA_ERR_IO;
+    return emit(buf, out, len);
+}
+
+int poasta_graph_to_gfa(const poasta_graph *h, int v1, char **out, size_t *len) {
+    std::string buf;
+    if (!graph_to_gfa(h->g, buf, v1 != 0)) return POASTA_ERR_IO;
+    return emit(buf, out, len);
+}
+
+int poasta_graph_save(const poasta_graph *h, char **out, size_t *len) {
+    std::string buf;
+    graph_to_poasta(h->g, buf);
+    return emit(buf, out, len);
+}
+
+int poasta_graph_load(const uint8_t *data, size_t len, poasta_graph **out) {
+    poasta_graph *h = new (std::nothrow) poasta_graph();
+    if (!h) return POASTA_ERR_IO;
+    if (!graph_from_poasta(data, len, h->g)) {
+        delete h;
+        return POASTA_ERR_IO;
+    }
+    *out = h;
+    return POASTA_OK;
+}
+
+int poasta_graph_from_fasta_msa(const char *fasta, size_t len, poasta_graph **out) {
+    poasta_graph *h = new (std::nothrow) poasta_graph();
+    if (!h) return POASTA_ERR_IO;
+    auto recs = parse_fasta(fasta, len);
+    GraphError e = graph_from_fasta_msa(recs, h->g);
+    if (e != GraphError::Ok) {
+        delete h;
+        return map_graph_error(e);
+    }
+    *out = h;
+    return POASTA_OK;
+}
+
+void poasta_free_buffer(void *p) { free(p); }
+
+const char *poasta_version(void) { return "poasta_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

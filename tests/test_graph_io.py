@@ -1,0 +1,114 @@
+"""Host graph model + writers (poasta_b200/csrc/poa_graph.hpp, poa_io.hpp) against the reference's
+own exact-value tests: tests/io_fasta.rs, src/io/fasta.rs:165-197, src/graphs/poa.rs:507-559,
+tests/io_graph.rs, tests/poa_graph.rs."""
+import numpy as np
+import pytest
+
+from poasta_b200 import AlignedPair, InvalidAlignment, POAGraph, WeightsUnequalSize
+
+
+def test_new_graph_is_empty():
+    # graphs/poa.rs:507-516
+    g = POAGraph()
+    assert g.is_empty() and g.node_count() == 0 and g.node_count_with_start_and_end() == 2
+    assert g.edge_count() == 0 and g.num_sequences() == 0
+
+
+def test_add_alignment_with_weights_basic():
+    # graphs/poa.rs:518-559
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACG", None, [1, 1, 1])
+    assert not g.is_empty() and g.node_count() == 3 and g.edge_count() == 2 and g.num_sequences() == 1
+    a = g.view_arrays()
+    topo = list(a["topo_order"])
+    assert topo[0] == a["start_node"] and topo[-1] == a["end_node"]
+    real = [v for v in topo if v not in (a["start_node"], a["end_node"])]
+    assert bytes(a["symbol"][real]) == b"ACG"
+    aln = [AlignedPair(real[0], 0), AlignedPair(real[1], 1), AlignedPair(real[2], 2)]
+    g.add_alignment_with_weights("seq2", b"ACG", aln, [1, 1, 1])
+    assert g.node_count() == 3 and g.edge_count() == 2 and g.num_sequences() == 2
+
+
+def test_poa_graph_to_fasta_basic():
+    # tests/io_fasta.rs:5-20 — pins neighbour order, DFS column order and the col-1 leading-gap quirk
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"AC", None)
+    g.add_alignment_with_weights("seq2", b"ACGT", None)
+    assert g.to_fasta() == b">seq1\n---AC\n>seq2\nACGT--\n"
+
+
+def test_poa_graph_to_fasta_empty():
+    # tests/io_fasta.rs:22-33
+    g = POAGraph()
+    g.add_alignment_with_weights("empty", b"", None, [])
+    assert g.to_fasta() == b">empty\n"
+
+
+def test_fasta_unit_test_in_io_module():
+    # src/io/fasta.rs:165-197: ACG then A-G aligned => rows ACG / A-G
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACG", None)
+    aln = [AlignedPair(2, 0), AlignedPair(4, 1)]
+    g.add_alignment_with_weights("seq2", b"AG", aln)
+    assert g.to_fasta() == b">seq1\nACG\n>seq2\nA-G\n"
+
+
+def test_weights_unequal_size():
+    g = POAGraph()
+    with pytest.raises(WeightsUnequalSize):
+        g.add_alignment_with_weights("s", b"ACG", None, [1, 1])
+
+
+def test_invalid_alignment():
+    # graphs/poa.rs:210-224: no valid query position for a non-empty sequence
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACG", None)
+    with pytest.raises(InvalidAlignment):
+        g.add_alignment_with_weights("seq2", b"ACG", [AlignedPair(2, None)])
+
+
+def test_save_load_roundtrip():
+    # tests/io_graph.rs:15-28: node/edge counts survive save -> load; here also the writers' bytes
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACGT", None)
+    g.add_alignment_with_weights("seq2", b"AGT", [AlignedPair(2, 0), AlignedPair(4, 1), AlignedPair(5, 2)])
+    g2 = POAGraph.load(g.save())
+    assert g2.node_count() == g.node_count() and g2.edge_count() == g.edge_count()
+    assert g2.to_fasta() == g.to_fasta()
+    assert g2.save() == g.save()
+
+
+def test_toposort_is_topological():
+    # tests/poa_graph.rs:50-95: ranks form a valid topological order
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACGTACGT", None)
+    g.add_alignment_with_weights("seq2", b"ACTTACGT", [AlignedPair(2 + i, i) for i in range(8)])
+    a = g.view_arrays()
+    rank = np.zeros(a["n_nodes"], np.int64)
+    rank[a["topo_order"]] = np.arange(a["n_nodes"])
+    for v in range(a["n_nodes"]):
+        for s in a["succ"][a["succ_off"][v]:a["succ_off"][v + 1]]:
+            assert rank[v] < rank[s]
+    assert a["topo_order"][0] == 0 and a["topo_order"][-1] == 1
+
+
+def test_gfa_small():
+    g = POAGraph()
+    g.add_alignment_with_weights("seq1", b"ACGT", None)
+    g.add_alignment_with_weights("seq2", b"AGT", [AlignedPair(2, 0), AlignedPair(4, 1), AlignedPair(5, 2)])
+    gfa = g.to_gfa().decode().splitlines()
+    assert gfa[0] == "H\tVN:Z:1.1"
+    segs = [l.split("\t")[2] for l in gfa if l.startswith("S")]
+    assert sorted(segs) == ["A", "C", "GT"]
+    assert sum(l.startswith("L") for l in gfa) == 3
+    walks = [l.split("\t") for l in gfa if l.startswith("W")]
+    assert [w[3] for w in walks] == ["seq1", "seq2"]
+    v1 = g.to_gfa(v1=True).decode().splitlines()
+    assert sum(l.startswith("P") for l in v1) == 2
+
+
+def test_fasta_msa_import_roundtrip():
+    # io/graph.rs:36-103
+    g = POAGraph.from_fasta_msa(b">a\nACGT\n>b\nA-GT\n>c\nATGT\n")
+    assert g.node_count() == 5 and g.num_sequences() == 3
+    assert g.to_fasta() == b">a\nACGT\n>b\nA-GT\n>c\nATGT\n"
