@@ -81,6 +81,8 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
 /* Timing of the device work of the last poasta_align_batch on this thread (CUDA events on the
  * launching stream): milliseconds of the fill+traceback kernels, number of launches, cells. */
 int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *cells);
+/* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
+int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* ---- POAGraph (graphs/poa.rs) -------------------------------------------------------------- */
 typedef struct poasta_graph poasta_graph; /* opaque POAGraph<u32> */

@@ -2,6 +2,9 @@
 from .errors import (CudaError, GraphError, InvalidAlignment, NoAlignment, PoastaError, Unsupported,
                      WeightsUnequalSize)
 from .graph import AlignedPair, POAGraph
+from .aligner import (AffineDijkstra, AffineMinGapCost, AffinePathAware, AlignmentType, AstarResult, GapAffine,
+                      PoastaAligner, align_batch, msa_batch)
 
-__all__ = ["POAGraph", "AlignedPair", "PoastaError", "WeightsUnequalSize", "InvalidAlignment", "GraphError",
+__all__ = ["POAGraph", "AlignedPair", "PoastaAligner", "GapAffine", "AlignmentType", "AffineDijkstra", "AffineMinGapCost",
+           "AffinePathAware", "AstarResult", "align_batch", "msa_batch", "PoastaError", "WeightsUnequalSize", "InvalidAlignment", "GraphError",
            "CudaError", "NoAlignment", "Unsupported"]

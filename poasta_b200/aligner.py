@@ -1,0 +1,152 @@
+"""Python mirror of the reference's aligner API (/root/reference/src/aligner/mod.rs:40-146) over the C ABI.
+
+    aligner = PoastaAligner(AffineMinGapCost(GapAffine(4, 2, 6)), AlignmentType.Global)
+    result = aligner.align(graph, b"ACGT")          # -> AstarResult(score, alignment, ...)
+    graph.add_alignment_with_weights("name", b"ACGT", result.alignment)
+
+``align`` runs on the GPU (device 0 unless given); there is no CPU path.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .errors import check
+from .graph import NONE, AlignedPair, POAGraph
+
+
+@dataclass(frozen=True)
+class GapAffine:
+    """GapAffine::new(cost_mismatch, cost_gap_extend, cost_gap_open) — note the reference's argument order
+    (aligner/scoring/gap_affine.rs:26-30)."""
+    cost_mismatch: int = 4
+    cost_gap_extend: int = 2
+    cost_gap_open: int = 6
+
+
+class AlignmentType:
+    """aligner/scoring/mod.rs:50-62; EndsFree here is the all-Unbounded variant the CLI builds (bin/poasta.rs:287-301)."""
+    Global = 0
+    EndsFree = 1
+
+
+@dataclass(frozen=True)
+class AffineDijkstra:
+    costs: GapAffine = GapAffine()
+    heuristic = 0
+
+
+@dataclass(frozen=True)
+class AffineMinGapCost:
+    costs: GapAffine = GapAffine()
+    heuristic = 1
+
+
+@dataclass(frozen=True)
+class AffinePathAware:
+    costs: GapAffine = GapAffine()
+    heuristic = 2
+
+
+@dataclass
+class AstarResult:
+    """aligner/astar.rs:81-90. num_queued/num_pruned are A*-specific and reported as 0; num_visited = DP cells."""
+    score: int
+    alignment: list
+    num_queued: int = 0
+    num_visited: int = 0
+    num_pruned: int = 0
+    rpos: np.ndarray = field(default=None, repr=False)
+    qpos: np.ndarray = field(default=None, repr=False)
+
+
+def _params(config, aln_type):
+    c = config.costs
+    return _lib.Params(c.cost_mismatch, c.cost_gap_open, c.cost_gap_extend, aln_type, config.heuristic)
+
+
+def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0):
+    """``poasta_align_batch``: independent (graph, query) problems in one device batch. Returns AstarResult list."""
+    lib = _lib.load()
+    n = len(queries)
+    views = (_lib.GraphView * len(graphs))()
+    for i, g in enumerate(graphs):
+        views[i] = g.view() if isinstance(g, POAGraph) else g
+    if graph_of_query is None:
+        graph_of_query = list(range(n))
+    qs = [bytes(q) for q in queries]
+    qptr = (C.c_char_p * n)(*qs)
+    qlens = (C.c_uint32 * n)(*[len(q) for q in qs])
+    goq = (C.c_uint32 * n)(*graph_of_query)
+    results = (_lib.Result * n)()
+    bufs = []
+    u32p = C.POINTER(C.c_uint32)
+    for i in range(n):
+        cap = views[graph_of_query[i]].n_nodes + len(qs[i]) + 2
+        r = np.empty(cap, np.uint32)
+        q = np.empty(cap, np.uint32)
+        bufs.append((r, q))
+        results[i].rpos = r.ctypes.data_as(u32p)
+        results[i].qpos = q.ctypes.data_as(u32p)
+        results[i].capacity = cap
+    prm = _params(config, aln_type)
+    check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
+    out = []
+    for i in range(n):
+        check(results[i].status, f"alignment {i}")
+        k = results[i].n_pairs
+        r, q = bufs[i][0][:k].copy(), bufs[i][1][:k].copy()
+        aln = [AlignedPair(None if a == NONE else int(a), None if b == NONE else int(b)) for a, b in zip(r, q)]
+        out.append(AstarResult(int(results[i].score), aln, 0, int(results[i].num_cells), 0, r, q))
+    return out
+
+
+def last_batch_stats():
+    lib = _lib.load()
+    ms, nl, cells = C.c_double(), C.c_uint32(), C.c_uint64()
+    lib.poasta_last_batch_stats(C.byref(ms), C.byref(nl), C.byref(cells))
+    return ms.value, nl.value, cells.value
+
+
+def last_batch_io():
+    lib = _lib.load()
+    a, b = C.c_uint64(), C.c_uint64()
+    lib.poasta_last_batch_io(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class PoastaAligner:
+    def __init__(self, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0):
+        self.config, self.aln_type, self.device = config, aln_type, device
+
+    def align(self, graph, seq):
+        return align_batch([graph], [seq], [0], self.config, self.aln_type, self.device)[0]
+
+
+def msa_batch(fastas, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0, graphs=None):
+    """``poasta align`` for many families at once (bin/poasta.rs:163-236): returns (graphs, scores per family, cells)."""
+    lib = _lib.load()
+    n = len(fastas)
+    fa = [f if isinstance(f, bytes) else f.encode() for f in fastas]
+    ptr = (C.c_char_p * n)(*fa)
+    lens = (C.c_size_t * n)(*[len(f) for f in fa])
+    nseq = [f.count(b">") for f in fa]
+    scores = np.zeros(max(1, sum(nseq)), np.uint32)
+    cells = C.c_uint64()
+    prm = _params(config, aln_type)
+    u32p = C.POINTER(C.c_uint32)
+    if graphs is None:
+        handles = (C.c_void_p * n)()
+        check(lib.poasta_msa_batch(device, ptr, lens, n, C.byref(prm), handles, scores.ctypes.data_as(u32p), C.byref(cells)),
+              "poasta_msa_batch")
+        graphs = [POAGraph(_handle=C.c_void_p(h)) for h in handles]
+    else:
+        handles = (C.c_void_p * n)(*[g._h for g in graphs])
+        check(lib.poasta_msa_batch_into(device, handles, ptr, lens, n, C.byref(prm), scores.ctypes.data_as(u32p),
+                                        C.byref(cells)), "poasta_msa_batch_into")
+    per_family, k = [], 0
+    for c in nseq:
+        per_family.append(scores[k:k + c].copy())
+        k += c
+    return graphs, per_family, cells.value

@@ -35,6 +35,13 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed building libposta_b200.so")
         with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
             f.write(r.stdout + r.stderr)
+    synth_so = os.path.join(HERE, "libsynth.so")
+    synth_src = os.path.join(CSRC, "synth.c")
+    if force or _stale(synth_so, [synth_src]):
+        r = subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", synth_so, synth_src], capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed building libsynth.so")
     cli_src = os.path.join(CSRC, "cli_main.cpp")
     if os.path.exists(cli_src) and (force or _stale(CLI, deps + [OUT])):
         cmd = ["g++", "-O2", "-std=c++17", "-o", CLI, cli_src, "-L" + HERE, "-lposta_b200",

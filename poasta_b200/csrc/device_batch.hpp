@@ -1,0 +1,135 @@
+// Host-side packing of (graph, query) problems into the flat, rank-ordered layout the kernels read.
+//
+// HBM layout (one batch):
+//   graphs[]      GraphDesc   per distinct graph: V, bases into the node / pred arrays
+//   node_sym[]    u8          symbol per RANK (row r of the DP = node topo_order[r])
+//   node_info[]   u32         per rank: successor summary used by openI_ok
+//                               bits 0-7  the unique successor symbol (valid if bit 9 set and bit 8 clear)
+//                               bit  8    "always open": an `end` successor or >= 2 distinct successor symbols
+//                               bit  9    has at least one successor
+//                               bit  10   row is the end node, bit 11 row is the start node
+//   node_id[]     u32         rank -> node id (for the emitted rpos)
+//   pred_off[]    u32         per graph V+1 offsets into pred_rank (absolute)
+//   pred_rank[]   u32         predecessor RANKS in the reference's Incoming order (graphs/poa.rs:433-435)
+//   queries[]     u8          query bytes, each padded to 4
+//   alns[]        AlnDesc     per alignment: graph id, Q, bases into queries / trace / output
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/poasta_b200.h"
+
+namespace poasta {
+
+struct GraphDesc {
+    uint32_t V;
+    uint32_t node_base;     // into node_sym / node_info / node_id
+    uint32_t predoff_base;  // into pred_off (V + 1 entries)
+    uint32_t max_in_degree;
+};
+
+struct AlnDesc {
+    uint32_t graph;
+    uint32_t Q;
+    uint32_t W;           // padded row width (multiple of 4, >= Q + 1)
+    uint32_t query_base;  // into queries
+    uint64_t trace_base;  // into the trace store (elements), V * W elements
+    uint32_t out_base;    // into the pair output staging area, capacity V + Q + 2
+    uint32_t out_cap;
+};
+
+constexpr uint32_t INFO_ALWAYS_OPEN = 1u << 8;
+constexpr uint32_t INFO_HAS_SUCC = 1u << 9;
+constexpr uint32_t INFO_IS_END = 1u << 10;
+constexpr uint32_t INFO_IS_START = 1u << 11;
+
+struct PackedBatch {
+    std::vector<GraphDesc> graphs;
+    std::vector<AlnDesc> alns;
+    std::vector<uint8_t> node_sym;
+    std::vector<uint32_t> node_info, node_id, pred_off, pred_rank;
+    std::vector<uint8_t> queries;
+    uint64_t trace_elems = 0;
+    uint64_t out_elems = 0;
+    uint64_t max_cells = 0;  // max over alignments of V * W
+    uint64_t total_cells = 0;  // sum of V_real * Q (the GCUPS numerator)
+    uint32_t max_in_degree = 0;
+
+    void clear() {
+        graphs.clear();
+        alns.clear();
+        node_sym.clear();
+        node_info.clear();
+        node_id.clear();
+        pred_off.clear();
+        pred_rank.clear();
+        queries.clear();
+        trace_elems = out_elems = max_cells = total_cells = 0;
+        max_in_degree = 0;
+    }
+
+    // Appends one graph; returns its id. `rank_scratch` avoids reallocation across calls.
+    uint32_t add_graph(const poasta_graph_view &g, std::vector<uint32_t> &rank_scratch) {
+        const uint32_t V = g.n_nodes;
+        rank_scratch.resize(V);
+        for (uint32_t r = 0; r < V; ++r) rank_scratch[g.topo_order[r]] = r;
+        GraphDesc gd;
+        gd.V = V;
+        gd.node_base = (uint32_t)node_sym.size();
+        gd.predoff_base = (uint32_t)pred_off.size();
+        gd.max_in_degree = 0;
+        for (uint32_t r = 0; r < V; ++r) {
+            const uint32_t v = g.topo_order[r];
+            node_sym.push_back(g.symbol[v]);
+            node_id.push_back(v);
+            uint32_t info = 0;
+            bool has_end = false, have_sym = false, multi = false;
+            uint8_t usym = 0;
+            for (uint32_t k = g.succ_off[v]; k < g.succ_off[v + 1]; ++k) {
+                const uint32_t s = g.succ[k];
+                info |= INFO_HAS_SUCC;
+                if (s == g.end_node) {
+                    has_end = true;
+                } else if (!have_sym) {
+                    usym = g.symbol[s];
+                    have_sym = true;
+                } else if (g.symbol[s] != usym) {
+                    multi = true;
+                }
+            }
+            if (has_end || multi) info |= INFO_ALWAYS_OPEN;
+            info |= usym;
+            if (v == g.end_node) info |= INFO_IS_END;
+            if (v == g.start_node) info |= INFO_IS_START;
+            node_info.push_back(info);
+            pred_off.push_back((uint32_t)pred_rank.size());
+            for (uint32_t k = g.pred_off[v]; k < g.pred_off[v + 1]; ++k) pred_rank.push_back(rank_scratch[g.pred[k]]);
+            gd.max_in_degree = std::max(gd.max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
+        }
+        pred_off.push_back((uint32_t)pred_rank.size());
+        max_in_degree = std::max(max_in_degree, gd.max_in_degree);
+        graphs.push_back(gd);
+        return (uint32_t)graphs.size() - 1;
+    }
+
+    void add_alignment(uint32_t graph, const uint8_t *q, uint32_t Q) {
+        AlnDesc a;
+        a.graph = graph;
+        a.Q = Q;
+        a.W = (Q + 1 + 3) & ~3u;
+        a.query_base = (uint32_t)queries.size();
+        queries.insert(queries.end(), q, q + Q);
+        while (queries.size() & 3) queries.push_back(0);
+        const uint64_t V = graphs[graph].V;
+        a.trace_base = trace_elems;
+        trace_elems += V * a.W;
+        a.out_cap = (uint32_t)V + Q + 2;
+        a.out_base = (uint32_t)out_elems;
+        out_elems += a.out_cap;
+        max_cells = std::max<uint64_t>(max_cells, V * a.W);
+        total_cells += (V - 2) * Q;
+        alns.push_back(a);
+    }
+};
+
+}  // namespace poasta
