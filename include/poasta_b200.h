@@ -29,7 +29,8 @@ typedef enum poasta_status {
     POASTA_ERR_GRAPH_CYCLE = -5,       /* PoastaError::GraphError from toposort (poa.rs:360)      */
     POASTA_ERR_NO_ALIGNMENT = -6,      /* panic!("Could not align sequence!") (aligner/astar.rs:143) */
     POASTA_ERR_UNSUPPORTED = -7,       /* mode/size outside what the device path implements       */
-    POASTA_ERR_IO = -8
+    POASTA_ERR_IO = -8,
+    POASTA_ERR_INTERNAL = -9           /* the DP score and the search score of one problem disagree */
 } poasta_status;
 
 /* GapAffine::new(mismatch, gap_extend, gap_open)  (aligner/scoring/gap_affine.rs:19-30) plus
@@ -39,7 +40,10 @@ typedef struct poasta_params {
     uint8_t gap_open;   /* -g, default 6 */
     uint8_t gap_extend; /* -e, default 2 */
     uint8_t mode;       /* 0 = Global, 1 = EndsFree{all Unbounded} (bin/poasta.rs:287-301) */
-    uint8_t heuristic;  /* 0 = dijkstra, 1 = mingap (default), 2 = path; accepted, see DESIGN.md */
+    uint8_t heuristic;  /* 0 = dijkstra, 1 = mingap (default), 2 = path (-H; changes which co-optimal path wins) */
+    uint8_t tiebreak;   /* 0 = reference-exact: DP score + order-exact search for the alignment (default);
+                           1 = DP only: optimal score, co-optimal alignment chosen by the backtrace priorities
+                               on the dense tables (fastest; may differ from the reference at ties) */
 } poasta_params;
 
 /* The `AlignableRefGraph` trait (graphs/mod.rs:23-53) flattened: what the aligner reads of a graph.
@@ -81,6 +85,8 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
 /* Timing of the device work of the last poasta_align_batch on this thread (CUDA events on the
  * launching stream): milliseconds of the fill+traceback kernels, number of launches, cells. */
 int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *cells);
+/* Milliseconds the order-exact search kernel took in the last call on this thread (0 with tiebreak = 1). */
+int poasta_last_batch_search_ms(double *search_ms);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 

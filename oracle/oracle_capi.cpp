@@ -13,6 +13,8 @@
 #include "../poasta_b200/csrc/poa_io.hpp"
 #include "astar_oracle.hpp"
 #include "dp_model.hpp"
+#include "../poasta_b200/csrc/replay_core.hpp"
+#include "../poasta_b200/csrc/search_index.hpp"
 
 using namespace oracle;
 
@@ -282,6 +284,46 @@ uint32_t dpmodel_align(const poasta_graph_view *view, const uint8_t *seq, uint32
         memcpy(tables_out + 2 * n, t.I.data(), n * 4);
     }
     return score;
+}
+
+// Host build of the product's order-exact search core (poasta_b200/csrc/replay_core.hpp), for CPU-side tests of the
+// logic that runs on the device. TEST HOOK ONLY: the product never executes this path (it has no CPU fallback).
+int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, int mode,
+                      int heuristic, uint32_t *score, uint32_t *rpos, uint32_t *qpos, uint32_t cap, uint32_t *n_pairs,
+                      uint64_t *stats) {
+    namespace rp = poasta::replay;
+    using rp::Item;
+    using rp::Params;
+    using rp::Result;
+    using rp::Scratch;
+    using rp::ScratchDims;
+    using rp::Search;
+    poasta::SearchIndex si;
+    si.build(*view, heuristic == 2);
+    rp::Graph g{view->n_nodes, view->start_node, view->end_node, view->succ_off, view->succ, view->pred_off, view->pred,
+            view->symbol, si.dist_min.data(), si.dist_max.data(), si.is_exit.data(), si.bub_off.data(), si.bub.data(),
+            si.path_off.empty() ? nullptr : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
+    ScratchDims d(view->n_nodes, qlen, x, o, e);
+    std::vector<uint32_t> blk((size_t)d.nbr * d.nbc, 0), qhead((size_t)d.f_max * 3, 0), reached((size_t)view->n_nodes * d.rw, 0),
+        dfa((size_t)(view->n_nodes + 2) * 3, 0);
+    const uint32_t max_blocks = d.nbr * d.nbc, max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
+    std::vector<uint4> cells((size_t)max_blocks * 48);
+    std::vector<Item> items(max_items);
+    Scratch s{blk.data(), (uint32_t *)cells.data(), qhead.data(), items.data(), reached.data(), dfa.data(),
+              d.nbc, d.rw, max_blocks, max_items, d.f_max};
+    Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
+    Search search(g, seq, qlen, p, s);
+    const uint32_t ocap = view->n_nodes + qlen + 2;
+    std::vector<uint32_t> out_r(ocap), out_q(ocap);
+    Result r = search.run(out_r.data(), out_q.data(), ocap);
+    *score = r.score;
+    *n_pairs = r.n_pairs;
+    for (uint32_t i = 0; i < r.n_pairs && i < cap; ++i) {
+        rpos[i] = out_r[ocap - r.n_pairs + i];
+        qpos[i] = out_q[ocap - r.n_pairs + i];
+    }
+    if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = search.n_blocks, stats[4] = search.n_items;
+    return r.status;
 }
 
 void oracle_free(void *p) { free(p); }

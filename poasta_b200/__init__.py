@@ -3,8 +3,8 @@ from .errors import (CudaError, GraphError, InvalidAlignment, NoAlignment, Poast
                      WeightsUnequalSize)
 from .graph import AlignedPair, POAGraph
 from .aligner import (AffineDijkstra, AffineMinGapCost, AffinePathAware, AlignmentType, AstarResult, GapAffine,
-                      PoastaAligner, align_batch, msa_batch)
+                      PoastaAligner, TIEBREAK_DP, TIEBREAK_EXACT, align_batch, msa_batch)
 
 __all__ = ["POAGraph", "AlignedPair", "PoastaAligner", "GapAffine", "AlignmentType", "AffineDijkstra", "AffineMinGapCost",
-           "AffinePathAware", "AstarResult", "align_batch", "msa_batch", "PoastaError", "WeightsUnequalSize", "InvalidAlignment", "GraphError",
+           "AffinePathAware", "AstarResult", "align_batch", "msa_batch", "TIEBREAK_EXACT", "TIEBREAK_DP", "PoastaError", "WeightsUnequalSize", "InvalidAlignment", "GraphError",
            "CudaError", "NoAlignment", "Unsupported"]

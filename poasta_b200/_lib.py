@@ -25,7 +25,7 @@ class GraphView(C.Structure):
 class Params(C.Structure):
     """``poasta_params``: GapAffine costs + AlignmentType + heuristic."""
     _fields_ = [("mismatch", C.c_uint8), ("gap_open", C.c_uint8), ("gap_extend", C.c_uint8),
-                ("mode", C.c_uint8), ("heuristic", C.c_uint8)]
+                ("mode", C.c_uint8), ("heuristic", C.c_uint8), ("tiebreak", C.c_uint8)]
 
 
 class Result(C.Structure):
@@ -37,7 +37,7 @@ class Result(C.Structure):
 
 # every symbol include/poasta_b200.h declares
 EXPORTS = [
-    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_batch_io",
+    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_batch_io", "poasta_last_batch_search_ms",
     "poasta_graph_new", "poasta_graph_free", "poasta_graph_node_count",
     "poasta_graph_node_count_with_start_and_end", "poasta_graph_edge_count",
     "poasta_graph_num_sequences", "poasta_graph_add_alignment", "poasta_graph_get_view",
@@ -80,6 +80,7 @@ def load():
     lib.poasta_align_batch.argtypes = [C.c_int, C.POINTER(GraphView), C.c_uint32, C.POINTER(C.c_char_p),
                                        u32p, u32p, C.c_uint32, C.POINTER(Params), C.POINTER(Result)]
     lib.poasta_last_batch_stats.argtypes = [C.POINTER(C.c_double), u32p, C.POINTER(C.c_uint64)]
+    lib.poasta_last_batch_search_ms.argtypes = [C.POINTER(C.c_double)]
     lib.poasta_last_batch_io.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.poasta_msa_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32,
                                      C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(C.c_uint64)]

@@ -61,12 +61,16 @@ class AstarResult:
     qpos: np.ndarray = field(default=None, repr=False)
 
 
-def _params(config, aln_type):
+TIEBREAK_EXACT, TIEBREAK_DP = 0, 1
+
+
+def _params(config, aln_type, tiebreak=TIEBREAK_EXACT):
     c = config.costs
-    return _lib.Params(c.cost_mismatch, c.cost_gap_open, c.cost_gap_extend, aln_type, config.heuristic)
+    return _lib.Params(c.cost_mismatch, c.cost_gap_open, c.cost_gap_extend, aln_type, config.heuristic, tiebreak)
 
 
-def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0):
+def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0,
+                tiebreak=TIEBREAK_EXACT):
     """``poasta_align_batch``: independent (graph, query) problems in one device batch. Returns AstarResult list."""
     lib = _lib.load()
     n = len(queries)
@@ -90,7 +94,7 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
         results[i].rpos = r.ctypes.data_as(u32p)
         results[i].qpos = q.ctypes.data_as(u32p)
         results[i].capacity = cap
-    prm = _params(config, aln_type)
+    prm = _params(config, aln_type, tiebreak)
     check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
     out = []
     for i in range(n):
@@ -109,6 +113,13 @@ def last_batch_stats():
     return ms.value, nl.value, cells.value
 
 
+def last_batch_search_ms():
+    lib = _lib.load()
+    ms = C.c_double()
+    lib.poasta_last_batch_search_ms(C.byref(ms))
+    return ms.value
+
+
 def last_batch_io():
     lib = _lib.load()
     a, b = C.c_uint64(), C.c_uint64()
@@ -117,14 +128,15 @@ def last_batch_io():
 
 
 class PoastaAligner:
-    def __init__(self, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0):
-        self.config, self.aln_type, self.device = config, aln_type, device
+    def __init__(self, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0, tiebreak=TIEBREAK_EXACT):
+        self.config, self.aln_type, self.device, self.tiebreak = config, aln_type, device, tiebreak
 
     def align(self, graph, seq):
-        return align_batch([graph], [seq], [0], self.config, self.aln_type, self.device)[0]
+        return align_batch([graph], [seq], [0], self.config, self.aln_type, self.device, self.tiebreak)[0]
 
 
-def msa_batch(fastas, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0, graphs=None):
+def msa_batch(fastas, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0, graphs=None,
+              tiebreak=TIEBREAK_EXACT):
     """``poasta align`` for many families at once (bin/poasta.rs:163-236): returns (graphs, scores per family, cells)."""
     lib = _lib.load()
     n = len(fastas)
@@ -134,7 +146,7 @@ def msa_batch(fastas, config=AffineMinGapCost(), aln_type=AlignmentType.Global, 
     nseq = [f.count(b">") for f in fa]
     scores = np.zeros(max(1, sum(nseq)), np.uint32)
     cells = C.c_uint64()
-    prm = _params(config, aln_type)
+    prm = _params(config, aln_type, tiebreak)
     u32p = C.POINTER(C.c_uint32)
     if graphs is None:
         handles = (C.c_void_p * n)()

@@ -31,6 +31,7 @@
 
 #include "device_batch.hpp"
 #include "graph_handle.hpp"
+#include "replay_kernel.cuh"
 
 namespace poasta {
 
@@ -415,6 +416,9 @@ struct DeviceContext {
     Buf graphs, alns, node_sym, node_info, node_id, pred_off, pred_rank, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
+    Buf r_graphs, r_sym, r_is_exit, r_dist_min, r_dist_max, r_succ_off, r_succ, r_pred_off, r_pred, r_bub_off, r_bub, r_path_off,
+        r_path_rem, r_slabs, r_stats;
+    PinBuf h_stats;
     double last_kernel_ms = 0;
     uint32_t last_launches = 0;
     uint64_t last_cells = 0;
@@ -446,7 +450,7 @@ static DeviceContext &ctx_for(int device) {
     return ctxs[device & 15];
 }
 
-static thread_local double tl_kernel_ms = 0;
+static thread_local double tl_kernel_ms = 0, tl_search_ms = 0;
 static thread_local uint32_t tl_launches = 0;
 static thread_local uint64_t tl_cells = 0;
 static thread_local uint64_t tl_h2d = 0, tl_d2h = 0;
@@ -585,15 +589,16 @@ struct Problem {
     uint32_t graph_key;  // problems with the same key share one packed graph
     const uint8_t *query;
     uint32_t qlen;
+    const SearchIndex *sidx;  // optional prebuilt index for the order-exact search (built on demand when null)
 };
 
-// Aligns all problems; calls sink(i, score, status, rpos*, qpos*, n_pairs) per problem in order.
+// DP path: aligns all problems; calls sink(i, score, status, rpos*, qpos*, n_pairs) per problem in order.
 template <class Sink>
-static int align_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
+static int dp_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
     DeviceContext &c = ctx_for(device);
     int rc = c.init(device);
     if (rc) return rc;
-    if (prm.mode != 0) return POASTA_ERR_UNSUPPORTED;  // ends-free: see DESIGN.md (reference terminates prematurely; not a DP optimum)
+    if (prm.mode != 0) return POASTA_ERR_UNSUPPORTED;  // ends-free is an order property of the reference's search, not a DP optimum
     const uint64_t budget = trace_budget_bytes();
     PackedBatch pb;
     std::vector<uint32_t> rank_scratch;
@@ -648,6 +653,234 @@ static int align_problems(int device, const std::vector<Problem> &probs, const p
     return 0;
 }
 
+// ---- order-exact search path ------------------------------------------------------------------------
+static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_params &prm, ChunkResult &res,
+                      std::vector<uint32_t> *stats_out) {
+    const uint32_t n = (uint32_t)pr.alns.size();
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c.device));
+    const replay::ScratchDims dmax(pr.max_V, pr.max_Q, prm.mismatch, prm.gap_open, prm.gap_extend);
+    auto up = [](uint64_t b) { return (b + 255) & ~(uint64_t)255; };
+    const uint64_t blk_entries = (uint64_t)dmax.nbr * dmax.nbc;
+    const uint64_t cells_per_aln = (uint64_t)pr.max_V * (pr.max_Q + 1);
+    uint64_t max_blocks = blk_entries;
+    uint64_t max_items = 262144 + cells_per_aln / 8;
+    uint64_t off_cells = up(blk_entries * 4);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, std::min<uint64_t>((uint64_t)64 << 30, total_b / 3));
+    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_reached = 0, off_dfa = 0;
+    auto layout = [&]() {
+        off_qhead = off_cells + up(max_blocks * 768);
+        off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
+        off_reached = off_items + up(max_items * 16);
+        off_dfa = off_reached + up((uint64_t)pr.max_V * dmax.rw * 4);
+        slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 12);
+    };
+    layout();
+    // keep at least 2 workers per SM resident: shrink the cell arena (the search touches a band of the table) before
+    // shrinking the worker count; exhausted arenas are reported per alignment (RP_OUT_OF_BLOCKS) and retried at full size
+    const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 32);
+    if (slab * want_workers > budget && max_blocks > 4096) {
+        const uint64_t fixed = slab - up(max_blocks * 768);
+        const uint64_t per = budget / want_workers;
+        uint64_t nb = per > fixed ? (per - fixed) / 768 : 0;
+        nb = std::max<uint64_t>(nb, std::min<uint64_t>(blk_entries, std::max<uint64_t>(4096, blk_entries / 4)));
+        max_blocks = std::min(max_blocks, nb);
+        layout();
+    }
+    uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
+    workers = ((workers + REPLAY_WARPS_PER_CTA - 1) / REPLAY_WARPS_PER_CTA) * REPLAY_WARPS_PER_CTA;
+    if (!c.r_slabs.reserve(workers * slab)) {
+        workers = REPLAY_WARPS_PER_CTA;
+        if (!c.r_slabs.reserve(workers * slab)) return POASTA_ERR_CUDA;
+    }
+    bool ok = c.r_graphs.reserve(pr.graphs.size() * sizeof(RGraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
+              c.r_sym.reserve(pr.sym.size() + 4) && c.r_is_exit.reserve(pr.is_exit.size() + 4) &&
+              c.queries.reserve(pr.queries.size() + 4) && c.r_dist_min.reserve(pr.dist_min.size() * 4 + 4) &&
+              c.r_dist_max.reserve(pr.dist_max.size() * 4 + 4) && c.r_succ_off.reserve(pr.succ_off.size() * 4 + 4) &&
+              c.r_succ.reserve(pr.succ.size() * 4 + 4) && c.r_pred_off.reserve(pr.pred_off.size() * 4 + 4) &&
+              c.r_pred.reserve(pr.pred.size() * 4 + 4) && c.r_bub_off.reserve(pr.bub_off.size() * 4 + 4) &&
+              c.r_bub.reserve(pr.bub.size() * 4 + 4) && c.r_path_off.reserve(pr.path_off.size() * 4 + 4) &&
+              c.r_path_rem.reserve(pr.path_rem.size() * 4 + 4) && c.scores.reserve(n * 4) && c.counter.reserve(4) &&
+              c.out_r.reserve(pr.out_elems * 4) && c.out_q.reserve(pr.out_elems * 4) && c.n_pairs.reserve(n * 4) &&
+              c.status.reserve(n * 4) && c.offsets.reserve((n + 1) * 4) && c.r_stats.reserve((size_t)n * 16);
+    if (!ok) return POASTA_ERR_CUDA;
+    cudaStream_t s = c.stream;
+    auto h2d = [&](Buf &b, const void *src, size_t bytes) -> cudaError_t {
+        tl_h2d += bytes;
+        return bytes ? cudaMemcpyAsync(b.d, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    CK(h2d(c.r_graphs, pr.graphs.data(), pr.graphs.size() * sizeof(RGraphDesc)));
+    CK(h2d(c.alns, pr.alns.data(), n * sizeof(AlnDesc)));
+    CK(h2d(c.r_sym, pr.sym.data(), pr.sym.size()));
+    CK(h2d(c.r_is_exit, pr.is_exit.data(), pr.is_exit.size()));
+    CK(h2d(c.queries, pr.queries.data(), pr.queries.size()));
+    CK(h2d(c.r_dist_min, pr.dist_min.data(), pr.dist_min.size() * 4));
+    CK(h2d(c.r_dist_max, pr.dist_max.data(), pr.dist_max.size() * 4));
+    CK(h2d(c.r_succ_off, pr.succ_off.data(), pr.succ_off.size() * 4));
+    CK(h2d(c.r_succ, pr.succ.data(), pr.succ.size() * 4));
+    CK(h2d(c.r_pred_off, pr.pred_off.data(), pr.pred_off.size() * 4));
+    CK(h2d(c.r_pred, pr.pred.data(), pr.pred.size() * 4));
+    CK(h2d(c.r_bub_off, pr.bub_off.data(), pr.bub_off.size() * 4));
+    CK(h2d(c.r_bub, pr.bub.data(), pr.bub.size() * 4));
+    CK(h2d(c.r_path_off, pr.path_off.data(), pr.path_off.size() * 4));
+    CK(h2d(c.r_path_rem, pr.path_rem.data(), pr.path_rem.size() * 4));
+    CK(cudaMemsetAsync(c.counter.d, 0, 4, s));
+
+    ReplayDev B;
+    B.graphs = (const RGraphDesc *)c.r_graphs.d;
+    B.alns = (const AlnDesc *)c.alns.d;
+    B.sym = (const uint8_t *)c.r_sym.d;
+    B.is_exit = (const uint8_t *)c.r_is_exit.d;
+    B.queries = (const uint8_t *)c.queries.d;
+    B.dist_min = (const uint32_t *)c.r_dist_min.d;
+    B.dist_max = (const uint32_t *)c.r_dist_max.d;
+    B.succ_off = (const uint32_t *)c.r_succ_off.d;
+    B.succ = (const uint32_t *)c.r_succ.d;
+    B.pred_off = (const uint32_t *)c.r_pred_off.d;
+    B.pred = (const uint32_t *)c.r_pred.d;
+    B.bub_off = (const uint32_t *)c.r_bub_off.d;
+    B.bub = (const uint32_t *)c.r_bub.d;
+    B.path_off = (const uint32_t *)c.r_path_off.d;
+    B.path_rem = (const uint32_t *)c.r_path_rem.d;
+    B.n_alns = n;
+    B.prm = replay::Params{prm.mismatch, prm.gap_open, prm.gap_extend, prm.mode, prm.heuristic};
+    B.slabs = (uint8_t *)c.r_slabs.d;
+    B.slab_bytes = slab;
+    B.off_cells = off_cells, B.off_qhead = off_qhead, B.off_items = off_items, B.off_reached = off_reached, B.off_dfa = off_dfa;
+    B.max_blocks = (uint32_t)max_blocks, B.max_items = (uint32_t)max_items;
+    B.counter = (uint32_t *)c.counter.d;
+    B.scores = (uint32_t *)c.scores.d;
+    B.n_pairs = (uint32_t *)c.n_pairs.d;
+    B.out_r = (uint32_t *)c.out_r.d;
+    B.out_q = (uint32_t *)c.out_q.d;
+    B.status = (int32_t *)c.status.d;
+    B.stats = (uint32_t *)c.r_stats.d;
+
+    BatchDev P;  // the fields the scan / compact kernels read
+    memset(&P, 0, sizeof P);
+    P.alns = B.alns, P.n_alns = n, P.out_r = B.out_r, P.out_q = B.out_q, P.n_pairs = B.n_pairs;
+
+    CK(cudaEventRecord(c.ev0, s));
+    replay_kernel<<<(unsigned)(workers / REPLAY_WARPS_PER_CTA), REPLAY_WARPS_PER_CTA * 32, 0, s>>>(B);
+    scan_kernel<<<1, 1024, 0, s>>>(B.n_pairs, (uint32_t *)c.offsets.d, n);
+    CK(cudaEventRecord(c.ev1, s));
+    CK(cudaGetLastError());
+    if (!c.h_scores.reserve(n * 4) || !c.h_npairs.reserve(n * 4) || !c.h_status.reserve(n * 4) || !c.h_offsets.reserve((n + 1) * 4) ||
+        !c.h_stats.reserve((size_t)n * 16))
+        return POASTA_ERR_CUDA;
+    CK(cudaMemcpyAsync(c.h_offsets.h, c.offsets.d, (n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_scores.h, c.scores.d, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_npairs.h, c.n_pairs.d, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_status.h, c.status.d, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_stats.h, c.r_stats.d, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t total_pairs = ((uint32_t *)c.h_offsets.h)[n];
+    if (!c.dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.dense_q.reserve((size_t)total_pairs * 4 + 4) ||
+        !c.h_dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.h_dense_q.reserve((size_t)total_pairs * 4 + 4))
+        return POASTA_ERR_CUDA;
+    compact_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(P, (const uint32_t *)c.offsets.d, (uint32_t *)c.dense_r.d,
+                                                       (uint32_t *)c.dense_q.d);
+    CK(cudaGetLastError());
+    if (total_pairs) {
+        CK(cudaMemcpyAsync(c.h_dense_r.h, c.dense_r.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c.h_dense_q.h, c.dense_q.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    tl_search_ms += ms;
+    tl_d2h += (uint64_t)(8 * n + 1) * 4 + (uint64_t)total_pairs * 8;
+    tl_launches += 3;
+    res.scores.assign((uint32_t *)c.h_scores.h, (uint32_t *)c.h_scores.h + n);
+    res.n_pairs.assign((uint32_t *)c.h_npairs.h, (uint32_t *)c.h_npairs.h + n);
+    res.offsets.assign((uint32_t *)c.h_offsets.h, (uint32_t *)c.h_offsets.h + n + 1);
+    res.status.assign((int32_t *)c.h_status.h, (int32_t *)c.h_status.h + n);
+    res.dense_r = (const uint32_t *)c.h_dense_r.h;
+    res.dense_q = (const uint32_t *)c.h_dense_q.h;
+    if (stats_out) stats_out->assign((uint32_t *)c.h_stats.h, (uint32_t *)c.h_stats.h + (size_t)n * 4);
+    return 0;
+}
+
+static int map_replay_status(int st) {
+    switch (st) {
+        case replay::RP_OK: return POASTA_OK;
+        case replay::RP_EMPTY_QUEUE:
+        case replay::RP_NO_BACKTRACE:
+        case replay::RP_SCORE_WRAP: return POASTA_ERR_NO_ALIGNMENT;  // the reference panics in these cases
+        default: return POASTA_ERR_UNSUPPORTED;                    // scratch arena exhausted
+    }
+}
+
+template <class Sink>
+static int replay_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
+    DeviceContext &c = ctx_for(device);
+    int rc = c.init(device);
+    if (rc) return rc;
+    PackedReplay pr;
+    ChunkResult res;
+    std::vector<size_t> idx;
+    SearchIndex tmp;
+    uint32_t last_key = 0xFFFFFFFFu, last_gid = 0;
+    for (size_t i = 0; i < probs.size(); ++i) {
+        const Problem &p = probs[i];
+        if (p.graph->n_nodes <= 2) continue;  // empty-graph shortcut handled below (aligner/mod.rs:124-142)
+        if (p.graph_key != last_key || pr.graphs.empty()) {
+            const SearchIndex *si = p.sidx;
+            if (!si) {
+                tmp.build(*p.graph, prm.heuristic == 2);
+                si = &tmp;
+            }
+            last_gid = pr.add_graph(*p.graph, *si);
+            last_key = p.graph_key;
+        }
+        pr.add_alignment(last_gid, p.query, p.qlen);
+        idx.push_back(i);
+    }
+    rc = run_replay(c, pr, prm, res, nullptr);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t i = 0; i < probs.size(); ++i) {
+        if (probs[i].graph->n_nodes <= 2) {
+            sink(i, probs[i].qlen * 4u, 0, (const uint32_t *)nullptr, (const uint32_t *)nullptr, 0u);
+            continue;
+        }
+        sink(i, res.scores[k], (int32_t)map_replay_status(res.status[k]), res.dense_r + res.offsets[k], res.dense_q + res.offsets[k],
+             res.n_pairs[k]);
+        ++k;
+    }
+    return 0;
+}
+
+// Dispatch on poasta_params::tiebreak (include/poasta_b200.h).
+template <class Sink>
+static int align_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
+    if (prm.tiebreak == 1) return dp_problems(device, probs, prm, sink);
+    if (prm.mode != 0) return replay_problems(device, probs, prm, sink);  // ends-free exists only as a search-order property
+    // reference-exact, global: the DP kernels give the optimal score of every problem, the search gives the alignment;
+    // the two scores must agree (device-side self check of both paths)
+    std::vector<uint32_t> dp_score(probs.size(), 0);
+    std::vector<int32_t> dp_status(probs.size(), 0);
+    poasta_params dp_prm = prm;
+    dp_prm.tiebreak = 1;
+    bool any_q0 = false;
+    for (const Problem &p : probs) any_q0 |= (p.qlen == 0);
+    int rc = 0;
+    if (!any_q0) {
+        rc = dp_problems(device, probs, dp_prm, [&](size_t i, uint32_t score, int32_t status, const uint32_t *, const uint32_t *, uint32_t) {
+            dp_score[i] = score;
+            dp_status[i] = status;
+        });
+        if (rc) return rc;
+    }
+    return replay_problems(device, probs, prm,
+                           [&](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
+                               if (!any_q0 && status == 0 && dp_status[i] == 0 && dp_score[i] != score) status = POASTA_ERR_INTERNAL;
+                               sink(i, score, status, r, q, np);
+                           });
+}
+
 }  // namespace poasta
 
 using namespace poasta;
@@ -658,12 +891,12 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
                        const uint32_t *qlens, const uint32_t *graph_of_query, uint32_t n_queries, const poasta_params *params,
                        poasta_result *results) {
     if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
-    tl_kernel_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
     std::vector<Problem> probs(n_queries);
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
         if (gi >= n_graphs) return POASTA_ERR_INVALID_ARG;
-        probs[i] = {&graphs[gi], gi, queries[i], qlens[i]};
+        probs[i] = {&graphs[gi], gi, queries[i], qlens[i], nullptr};
     }
     return align_problems(device, probs, *params,
                           [&](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
@@ -690,6 +923,11 @@ int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *c
     return 0;
 }
 
+int poasta_last_batch_search_ms(double *search_ms) {
+    if (search_ms) *search_ms = tl_search_ms;
+    return 0;
+}
+
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = tl_h2d;
     if (d2h_bytes) *d2h_bytes = tl_d2h;
@@ -700,7 +938,7 @@ int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
 int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *fasta, const size_t *fasta_len,
                           uint32_t n_families, const poasta_params *params, uint32_t *scores_out, uint64_t *cells_out) {
     if (!graphs || !fasta || !fasta_len || !params) return POASTA_ERR_INVALID_ARG;
-    tl_kernel_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
     std::vector<std::vector<FastaRecord>> recs(n_families);
     std::vector<size_t> score_base(n_families + 1, 0);
     size_t max_round = 0;
@@ -757,10 +995,16 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
             }
         }
         if (to_align.empty()) continue;
-        parallel_for(to_align.size(), [&](size_t k) { views[to_align[k]] = graphs[to_align[k]]->flat_view(); });
+        const bool need_index = params->tiebreak == 0;
+        parallel_for(to_align.size(), [&](size_t k) {
+            poasta_graph *h = graphs[to_align[k]];
+            views[to_align[k]] = h->flat_view();
+            if (need_index) h->search_index(params->heuristic == 2);
+        });
         for (uint32_t f : to_align) {
             const FastaRecord &rec = recs[f][round];
-            probs.push_back({&views[f], f, (const uint8_t *)rec.seq.data(), (uint32_t)rec.seq.size()});
+            probs.push_back({&views[f], f, (const uint8_t *)rec.seq.data(), (uint32_t)rec.seq.size(),
+                             need_index ? &graphs[f]->sidx : nullptr});
             fam_of_prob.push_back(f);
             cells += (uint64_t)graphs[f]->g.node_count() * rec.seq.size();
         }

@@ -1,0 +1,606 @@
+// Order-exact search: reproduces which co-optimal alignment the reference returns.
+//
+// POASTA's result is not "the DP optimum + a fixed traceback priority": its backtrace tests score
+// equality against the sparse table of states its A* happened to record, and which co-optimal cells
+// are recorded depends on bucket pop order (Match, then Deletion, then Insertion, LIFO inside each),
+// greedy match extension and strict-improvement bubble pruning (SURVEY.md findings 2-3, A.4-A.9).
+// The dense DP kernels (align.cu) give the exact optimal score; this routine gives the reference's
+// exact alignment by running the same state machine with the same ordering rules:
+//   search loop            /root/reference/src/aligner/astar.rs:124-225
+//   greedy match extension /root/reference/src/aligner/dfa.rs:138-250
+//   transitions            /root/reference/src/aligner/scoring/gap_affine.rs:307-430
+//   bucket queue           /root/reference/src/aligner/queue.rs:31-70 + gap_affine.rs:945-966
+//   prune test             /root/reference/src/bubbles/reached.rs:38-255 + gap_affine.rs:780-792
+//   heuristics             /root/reference/src/aligner/heuristic.rs:40-184
+//   backtrace              /root/reference/src/aligner/scoring/gap_affine.rs:550-657, 804-915
+//
+// Device mapping: the state machine is sequential per alignment, so one warp owns one alignment and
+// lane 0 drives it (10^4 families in flight = 10^4 warps); all mutable state lives in a per-warp
+// scratch slab in HBM laid out for single-transaction accesses:
+//   visited table   two-level: u32 block pointers per (node>>3, offset>>3), 8x8-cell blocks of
+//                   {M, D, I} u32 scores allocated on first touch (what the reference hashes)
+//   bucket queue    per priority three LIFO stacks threaded through a 16-byte item array
+//   reached sets    one bitmap row per node (the reference's BTreeSet<offset> per bubble exit)
+// The same source compiles for the host (tests only) so the logic can be checked without a GPU.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define RP_HD __host__ __device__ __forceinline__
+#else
+#define RP_HD inline
+struct alignas(16) uint4 {
+    uint32_t x, y, z, w;
+};
+#endif
+
+namespace poasta {
+namespace replay {
+
+constexpr uint32_t UNV = 0xFFFFFFFFu;  // Score::Unvisited
+enum : uint32_t { ST_M = 0, ST_D = 1, ST_I = 2 };
+enum : int { RP_OK = 0, RP_EMPTY_QUEUE = 1, RP_NO_BACKTRACE = 2, RP_SCORE_WRAP = 3, RP_OUT_OF_BLOCKS = 4, RP_OUT_OF_ITEMS = 5,
+             RP_PRIORITY_RANGE = 6, RP_OUT_OF_PAIRS = 7 };
+
+struct Graph {  // node-id space, adjacency in the reference's order
+    uint32_t V, start, end;
+    const uint32_t *succ_off, *succ, *pred_off, *pred;
+    const uint8_t *sym;
+    const uint32_t *dist_min, *dist_max;
+    const uint8_t *is_exit;
+    const uint32_t *bub_off, *bub;      // triples
+    const uint32_t *path_off, *path_rem;  // may be null unless heuristic == 2
+};
+
+struct Item {
+    uint32_t score, node, offset, next;
+};
+
+struct Scratch {  // one slab per in-flight alignment
+    uint32_t *blk;       // block pointer table, nbr * nbc entries (0 = not allocated, else block index + 1)
+    uint32_t *cells;     // max_blocks * 192 u32
+    uint32_t *qhead;     // f_max * 3 stack heads (0 = empty, else item index + 1)
+    Item *items;         // max_items
+    uint32_t *reached;   // V * rw bitmap words
+    uint32_t *dfa;       // (V + 2) * 3
+    uint32_t nbc, rw, max_blocks, max_items, f_max;  // rw = row stride in words; word rw-1 of a row is its non-empty flag
+};
+
+struct Params {
+    uint32_t x, o, e;
+    int mode;       // 0 global, 1 ends-free (all bounds Unbounded)
+    int heuristic;  // 0 dijkstra, 1 mingap, 2 path
+};
+
+struct Result {
+    uint32_t score;
+    uint32_t n_pairs;  // pairs are written BACKWARDS from out_r[cap-1]; the alignment is out_r[cap-n .. cap)
+    int status;
+    uint32_t num_queued, num_visited, num_pruned;
+};
+
+struct Search {
+    const Graph &g;
+    const uint8_t *q;
+    const uint32_t Q;
+    const Params &p;
+    Scratch &s;
+    uint32_t n_blocks = 0, n_items = 0, free_items = 0;  // free_items: LIFO list of popped item slots (index + 1)
+    uint32_t f_cur = 0, f_hi = 0;
+    bool q_empty = true;
+    int err = RP_OK;
+
+    RP_HD Search(const Graph &g_, const uint8_t *q_, uint32_t Q_, const Params &p_, Scratch &s_) : g(g_), q(q_), Q(Q_), p(p_), s(s_) {}
+
+    RP_HD bool sym_eq(uint32_t node, uint8_t c) const { return node == g.end || g.sym[node] == c; }
+
+    // ---- visited table -------------------------------------------------------------------------
+    RP_HD uint32_t *cell(uint32_t node, uint32_t off, bool create) {
+        uint32_t *bp = s.blk + (size_t)(node >> 3) * s.nbc + (off >> 3);
+        uint32_t b = *bp;
+        if (b == 0) {
+            if (!create) return nullptr;
+            if (n_blocks >= s.max_blocks) {
+                err = RP_OUT_OF_BLOCKS;
+                return nullptr;
+            }
+            uint4 *c = reinterpret_cast<uint4 *>(s.cells + (size_t)n_blocks * 192);
+            for (int i = 0; i < 48; ++i) c[i] = uint4{UNV, UNV, UNV, UNV};
+            b = ++n_blocks;
+            *bp = b;
+        }
+        return s.cells + (size_t)(b - 1) * 192 + ((node & 7) * 8 + (off & 7)) * 3;
+    }
+    RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) {
+        const uint32_t *c = cell(node, off, false);
+        return c ? c[st] : UNV;
+    }
+    RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
+        uint32_t *c = cell(node, off, true);
+        if (c) c[st] = v;
+    }
+    RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
+        uint32_t *c = cell(node, off, true);
+        if (!c) return false;
+        if (v < c[st]) {
+            c[st] = v;
+            return true;
+        }
+        return false;
+    }
+
+    // ---- score arithmetic with the reference's NonMaxU32 / wrapping behaviour -------------------------
+    RP_HD uint32_t add(uint32_t a, uint32_t b) {
+        if (a == UNV) err = RP_SCORE_WRAP;
+        const uint32_t r = a + b;
+        if (r == UNV) err = RP_SCORE_WRAP;
+        return r;
+    }
+    RP_HD uint32_t sub(uint32_t a, uint32_t b) {
+        const uint32_t r = a - b;
+        if (r == UNV) err = RP_SCORE_WRAP;
+        return r;
+    }
+    RP_HD uint32_t gap_cost(uint32_t st, uint32_t len) const {
+        if (len == 0) return 0;
+        return (st == ST_M ? p.o : 0) + len * p.e;
+    }
+
+    // ---- heuristic ----------------------------------------------------------------------------------
+    RP_HD uint32_t h(uint32_t node, uint32_t off, uint32_t st) const {
+        if (p.heuristic == 0) return 0;
+        if (p.heuristic == 1) {
+            const uint32_t a = g.dist_min[node], b = g.dist_max[node];
+            const uint32_t tmin = off + (a ? a - 1 : 0), tmax = off + (b ? b - 1 : 0);
+            if (tmin > Q) return gap_cost(st == ST_D ? ST_D : ST_M, tmin - Q);
+            if (tmax < Q) return gap_cost(st == ST_I ? ST_I : ST_M, Q - tmax);
+            return 0;
+        }
+        const uint32_t rem_q = Q > off ? Q - off : 0;
+        const uint32_t b = g.path_off[node], e = g.path_off[node + 1];
+        if (b == e) return gap_cost(st, rem_q);
+        uint32_t best = UNV;
+        for (uint32_t k = b; k < e; ++k) {
+            const uint32_t rem_p = g.path_rem[k];
+            uint32_t c = 0;
+            if (rem_p > rem_q) c = gap_cost(st == ST_D ? ST_D : ST_M, rem_p - rem_q);
+            else if (rem_q > rem_p) c = gap_cost(st == ST_I ? ST_I : ST_M, rem_q - rem_p);
+            if (c < best) best = c;
+        }
+        return best;
+    }
+
+    // ---- bucket queue ---------------------------------------------------------------------------------
+    RP_HD void push(uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+        const uint32_t f = score + h(node, off, st);
+        if (f >= s.f_max) {
+            err = RP_PRIORITY_RANGE;
+            return;
+        }
+        uint32_t slot;
+        if (free_items) {
+            slot = free_items - 1;
+            free_items = s.items[slot].next;
+        } else {
+            if (n_items >= s.max_items) {
+                err = RP_OUT_OF_ITEMS;
+                return;
+            }
+            slot = n_items++;
+        }
+        uint32_t *head = s.qhead + (size_t)f * 3 + st;
+        s.items[slot] = Item{score, node, off, *head};
+        *head = slot + 1;
+        if (q_empty) {
+            f_cur = f_hi = f;
+            q_empty = false;
+        } else {
+            if (f < f_cur) f_cur = f;
+            if (f > f_hi) f_hi = f;
+        }
+    }
+    RP_HD bool pop(Item &out, uint32_t &st) {
+        if (q_empty) return false;
+        for (;;) {
+            uint32_t *head = s.qhead + (size_t)f_cur * 3;
+            for (uint32_t k = 0; k < 3; ++k) {  // Match, then Deletion, then Insertion
+                if (head[k]) {
+                    const uint32_t slot = head[k] - 1;
+                    out = s.items[slot];
+                    head[k] = out.next;
+                    s.items[slot].next = free_items;
+                    free_items = slot + 1;
+                    st = k;
+                    return true;
+                }
+            }
+            if (f_cur >= f_hi) {
+                q_empty = true;
+                return false;
+            }
+            ++f_cur;
+        }
+    }
+
+    // ---- reached sets (BTreeSet<offset> per exit) --------------------------------------------------------
+    RP_HD void mark_reached(uint32_t node, uint32_t off, uint32_t st) {
+        if (st == ST_M && g.is_exit[node]) {
+            uint32_t *row = s.reached + (size_t)node * s.rw;
+            row[off >> 5] |= 1u << (off & 31);
+            row[s.rw - 1] = 1;
+        }
+    }
+    // largest member < lim, or UNV
+    RP_HD uint32_t reached_prev(const uint32_t *row, uint32_t lim) const {
+        if (lim == 0) return UNV;
+        uint32_t i = lim - 1;
+        if ((i >> 5) >= s.rw - 1) i = (s.rw - 1) * 32 - 1;
+        int w = (int)(i >> 5);
+        uint32_t bits = row[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
+        for (;;) {
+            if (bits) {
+#if defined(__CUDA_ARCH__)
+                return (uint32_t)w * 32 + (31 - __clz(bits));
+#else
+                return (uint32_t)w * 32 + (31 - __builtin_clz(bits));
+#endif
+            }
+            if (--w < 0) return UNV;
+            bits = row[w];
+        }
+    }
+    // smallest member >= lim, or UNV
+    RP_HD uint32_t reached_next(const uint32_t *row, uint32_t lim) const {
+        uint32_t w = lim >> 5;
+        if (w >= s.rw - 1) return UNV;
+        uint32_t bits = row[w] & (0xFFFFFFFFu << (lim & 31));
+        for (;;) {
+            if (bits) {
+#if defined(__CUDA_ARCH__)
+                return w * 32 + (__ffs(bits) - 1);
+#else
+                return w * 32 + __builtin_ctz(bits);
+#endif
+            }
+            if (++w >= s.rw - 1) return UNV;
+            bits = row[w];
+        }
+    }
+
+    // reached.rs:191-255
+    RP_HD bool can_improve_at(uint32_t exit, uint32_t off, uint32_t score, uint32_t left, uint32_t right, uint32_t min_dist_to_end) {
+        uint32_t implicit;
+        if (left != UNV && right != UNV) {
+            const uint32_t il = add(get(exit, left, ST_M), gap_cost(ST_M, off - left));
+            const uint32_t gr = right - off;
+            const uint32_t ir = add(get(exit, right, ST_M), gap_cost(ST_M, gr));
+            implicit = gr > min_dist_to_end ? il : (il < ir ? il : ir);
+        } else if (right != UNV) {
+            const uint32_t gr = right - off;
+            const uint32_t ir = add(get(exit, right, ST_M), gap_cost(ST_M, gr));
+            if (gr > min_dist_to_end) return true;
+            implicit = ir;
+        } else if (left != UNV) {
+            implicit = add(get(exit, left, ST_M), gap_cost(ST_M, off - left));
+        } else {
+            return true;
+        }
+        return score < implicit;
+    }
+
+    // reached.rs:38-189
+    RP_HD bool can_improve_bubble(uint32_t exit, uint32_t min_d, uint32_t max_d, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+        const uint32_t *row = s.reached + (size_t)exit * s.rw;
+        // is_empty(): any reached offset at this exit
+        if (row[s.rw - 1] == 0) return true;
+        if (node == exit) return true;
+        const uint32_t tmin = off + min_d, tmax = off + max_d;
+        const uint32_t a = g.dist_min[exit];
+        const uint32_t mde = a ? a - 1 : 0;
+        if (tmax > Q) return true;
+        uint32_t prev = reached_prev(row, tmin);
+        bool have_last = false;
+        uint32_t last = 0;
+        for (uint32_t nx = reached_next(row, tmin); nx != UNV && nx <= tmax; nx = reached_next(row, nx + 1)) {
+            const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
+            if (st == ST_D) {
+                if (add(get(exit, nx, ST_M), p.o) > score) return true;
+            }
+            if (prev != UNV && st == ST_I) {
+                if (add(get(exit, prev, ST_M), p.o) > score) return true;
+            }
+            if (can_improve_at(exit, o1, score, prev, nx, mde)) return true;
+            uint32_t o2 = nx - 1u;  // wraps for nx == 0 like the release build
+            if (o2 < tmin) o2 = tmin;
+            if (o2 > tmax) o2 = tmax;
+            if (o2 != o1 && can_improve_at(exit, o2, score, prev, nx, mde)) return true;
+            prev = nx;
+            last = o2;
+            have_last = true;
+        }
+        const uint32_t next = reached_next(row, tmax == UNV ? tmax : tmax + 1);
+        if (!have_last && can_improve_at(exit, tmin, score, prev, next, mde)) return true;
+        if ((!have_last || last < tmax) && can_improve_at(exit, tmax, score, prev, next, mde)) return true;
+        if (prev != UNV && st == ST_I) {
+            if (add(get(exit, prev, ST_M), p.o) > score) return true;
+        }
+        return false;
+    }
+
+    RP_HD bool prune(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
+        for (uint32_t k = g.bub_off[node]; k < g.bub_off[node + 1]; ++k)
+            if (!can_improve_bubble(g.bub[3 * k], g.bub[3 * k + 1], g.bub[3 * k + 2], node, off, st, score)) return true;
+        return false;
+    }
+
+    RP_HD bool is_end(uint32_t node, uint32_t off, uint32_t st) const {  // gap_affine.rs:185-248, Unbounded bounds
+        if (p.mode == 0) return st == ST_M && node == g.end && off == Q;
+        return st == ST_M && (off > 0 || Q == 0);
+    }
+
+    // ---- backtrace (gap_affine.rs:550-657) ------------------------------------------------------------------
+    RP_HD bool bt(uint32_t node, uint32_t off, uint32_t st, uint32_t &bn, uint32_t &bo, uint32_t &bs) {
+        const uint32_t cur = get(node, off, st);
+        if (cur == UNV) return false;
+        if (st == ST_M) {
+            if (off > 0) {
+                const bool me = sym_eq(node, q[off - 1]) || node == g.end;
+                const uint32_t po = node == g.end ? off : off - 1;
+                const uint32_t want = me ? cur : sub(cur, p.x);
+                for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+                    if (get(g.pred[k], po, ST_M) == want) {
+                        bn = g.pred[k], bo = po, bs = ST_M;
+                        return true;
+                    }
+            }
+            if (get(node, off, ST_D) == cur) {
+                bn = node, bo = off, bs = ST_D;
+                return true;
+            }
+            if (get(node, off, ST_I) == cur) {
+                bn = node, bo = off, bs = ST_I;
+                return true;
+            }
+        } else if (st == ST_D) {
+            const uint32_t w1 = sub(sub(cur, p.o), p.e), w2 = sub(cur, p.e);
+            for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+                if (get(g.pred[k], off, ST_M) == w1) {
+                    bn = g.pred[k], bo = off, bs = ST_M;
+                    return true;
+                }
+            for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+                if (get(g.pred[k], off, ST_D) == w2) {
+                    bn = g.pred[k], bo = off, bs = ST_D;
+                    return true;
+                }
+        } else if (off > 0) {
+            if (get(node, off - 1, ST_M) == sub(sub(cur, p.o), p.e) || get(node, off - 1, ST_I) == sub(cur, p.e)) {
+                bn = node, bo = off - 1, bs = ST_M;  // both cases resume in Match state (gap_affine.rs:639-650)
+                return true;
+            }
+        }
+        return false;
+    }
+
+    // The whole alignment (astar.rs:108-226 + mod.rs:114-145 non-empty graph).
+    RP_HD Result run(uint32_t *out_r, uint32_t *out_q, uint32_t cap) {
+        Result res{0, 0, RP_OK, 0, 0, 0};
+        const uint32_t oe = p.o + p.e, oe8 = (p.o + p.e) & 0xFF;  // the queued delta is a u8 sum in the reference
+        if (p.mode == 0) {
+            push(g.start, 0, ST_M, 0);
+            set(g.start, 0, ST_M, 0);
+            ++res.num_queued;
+        } else {
+            bool any = false;
+            for (uint32_t n = g.V; n-- > 0;)
+                if (n != g.start && n != g.end) {
+                    push(n, 0, ST_M, 0);
+                    set(n, 0, ST_M, 0);
+                    ++res.num_queued;
+                    any = true;
+                }
+            if (!any) {
+                push(g.start, 0, ST_M, 0);
+                set(g.start, 0, ST_M, 0);
+                ++res.num_queued;
+            }
+        }
+        uint32_t end_score = 0, end_node = 0, end_off = 0;
+        bool done = false;
+        while (!done && err == RP_OK) {
+            Item it;
+            uint32_t st;
+            if (!pop(it, st)) {
+                err = RP_EMPTY_QUEUE;
+                break;
+            }
+            if (it.score > get(it.node, it.offset, st)) continue;
+            if (is_end(it.node, it.offset, st)) {
+                ++res.num_visited;
+                end_score = it.score, end_node = it.node, end_off = it.offset;
+                break;
+            }
+            if (prune(it.score, it.node, it.offset, st)) {
+                ++res.num_pruned;
+                continue;
+            }
+            mark_reached(it.node, it.offset, st);
+            ++res.num_visited;
+            const uint32_t score = it.score;
+            if (st == ST_M) {
+                // depth-first greedy match extension (dfa.rs:138-250); frames = (node, offset, next successor slot)
+                uint32_t depth = 1;
+                uint32_t *F = s.dfa;
+                F[0] = it.node, F[1] = it.offset, F[2] = g.succ_off[it.node];
+                uint32_t dfa_visited = 0;
+                while (depth > 0 && err == RP_OK) {
+                    // offset-0 special case, evaluated on every resume while a single frame is on the stack (dfa.rs:145-168)
+                    bool virtual_end = false;
+                    uint32_t v_parent = 0;
+                    if (depth == 1 && Q != 0 && F[1] == 0 && sym_eq(F[0], q[0])) {
+                        if (relax(F[0], 1, ST_M, score)) {
+                            v_parent = F[0];
+                            F[1] = 1, F[2] = g.succ_off[F[0]];
+                            mark_reached(F[0], 1, ST_M);
+                            ++dfa_visited;
+                            if (Q == 1) virtual_end = true;
+                        }
+                    }
+                    int kind = 0;  // 0 exhausted, 1 ref-graph end, 2 query end, 3 match, 4 mismatch
+                    uint32_t pn, po, cn = 0, co = 0;
+                    if (virtual_end) {
+                        kind = 1, pn = v_parent, po = 0, cn = v_parent, co = 1;
+                    } else {
+                        uint32_t *fr = F + (size_t)(depth - 1) * 3;
+                        pn = fr[0], po = fr[1];
+                        const uint32_t se = g.succ_off[pn + 1];
+                        while (fr[2] < se) {
+                            const uint32_t child = g.succ[fr[2]++];
+                            if (child == g.end) {
+                                relax(child, po, ST_M, score);
+                                kind = 1, cn = child, co = po;
+                                break;
+                            }
+                            if (po >= Q) {
+                                kind = 2, cn = child;
+                                break;
+                            }
+                            if (sym_eq(child, q[po])) {
+                                if (relax(child, po + 1, ST_M, score)) {
+                                    kind = 3, cn = child, co = po + 1;
+                                    break;
+                                }
+                            } else {
+                                kind = 4, cn = child, co = po + 1;
+                                break;
+                            }
+                        }
+                    }
+                    if (kind == 0) {
+                        --depth;
+                    } else if (kind == 3) {
+                        if (prune(score, cn, co, ST_M)) continue;
+                        mark_reached(cn, co, ST_M);
+                        ++dfa_visited;
+                        uint32_t *nf = F + (size_t)depth * 3;
+                        nf[0] = cn, nf[1] = co, nf[2] = g.succ_off[cn];
+                        ++depth;
+                    } else if (kind == 1) {
+                        if (is_end(cn, co, ST_M)) {
+                            end_score = score, end_node = cn, end_off = co;
+                            done = true;
+                            break;
+                        }
+                        if (relax(pn, po + 1, ST_I, add(add(score, p.o), p.e))) {  // gap_affine.rs:346-367
+                            push(pn, po + 1, ST_I, add(score, oe8));
+                            ++res.num_queued;
+                        }
+                    } else if (kind == 2) {
+                        if (relax(cn, po, ST_D, add(add(score, p.o), p.e))) {  // gap_affine.rs:369-391
+                            push(cn, po, ST_D, add(score, oe8));
+                            ++res.num_queued;
+                        }
+                    } else {  // mismatch: gap_affine.rs:393-430
+                        if (relax(cn, co, ST_M, add(score, p.x))) {
+                            push(cn, co, ST_M, add(score, p.x));
+                            ++res.num_queued;
+                        }
+                        const uint32_t ns = add(add(score, p.o), p.e);
+                        if (relax(pn, po + 1, ST_I, ns)) {
+                            push(pn, po + 1, ST_I, add(score, oe8));
+                            ++res.num_queued;
+                        }
+                        if (relax(cn, po, ST_D, ns)) {
+                            push(cn, po, ST_D, add(score, oe8));
+                            ++res.num_queued;
+                        }
+                    }
+                }
+                if (!done) res.num_visited += dfa_visited;
+            } else if (st == ST_I) {  // gap_affine.rs:307-322
+                if (relax(it.node, it.offset, ST_M, score)) {
+                    push(it.node, it.offset, ST_M, score);
+                    ++res.num_queued;
+                }
+                if (it.offset < Q && relax(it.node, it.offset + 1, ST_I, add(score, p.e))) {
+                    push(it.node, it.offset + 1, ST_I, add(score, p.e));
+                    ++res.num_queued;
+                }
+            } else {  // gap_affine.rs:323-341
+                if (relax(it.node, it.offset, ST_M, score)) {
+                    push(it.node, it.offset, ST_M, score);
+                    ++res.num_queued;
+                }
+                for (uint32_t k = g.succ_off[it.node]; k < g.succ_off[it.node + 1]; ++k)
+                    if (relax(g.succ[k], it.offset, ST_D, add(score, p.e))) {
+                        push(g.succ[k], it.offset, ST_D, add(score, p.e));
+                        ++res.num_queued;
+                    }
+            }
+        }
+        (void)oe;
+        res.score = end_score;
+        if (err != RP_OK) {
+            res.status = err;
+            return res;
+        }
+        // backtrace (gap_affine.rs:804-915), pairs written backwards from out[cap-1]
+        uint32_t pos = cap;
+        if (Q == 0) {
+        } else if (Q == 1 && end_off == 1 && sym_eq(end_node, q[0])) {
+            out_r[--pos] = end_node;
+            out_q[pos] = 0;
+        } else {
+            uint32_t cn, co, cs;
+            bool ok = bt(end_node, end_off, ST_M, cn, co, cs) || bt(end_node, end_off, ST_I, cn, co, cs) ||
+                      bt(end_node, end_off, ST_D, cn, co, cs);
+            if (!ok) {
+                if (Q <= 3) {
+                    for (uint32_t i = Q; i-- > 0;) {
+                        out_r[--pos] = end_node;
+                        out_q[pos] = i;
+                    }
+                } else {
+                    err = RP_NO_BACKTRACE;
+                }
+            } else {
+                uint32_t bn, bo, bs;
+                while (err == RP_OK && bt(cn, co, cs, bn, bo, bs)) {
+                    if (cs == ST_M && bs != ST_M) {
+                        cn = bn, co = bo, cs = bs;
+                        continue;
+                    }
+                    if (pos == 0) {
+                        err = RP_OUT_OF_PAIRS;
+                        break;
+                    }
+                    --pos;
+                    if (cs == ST_M) out_r[pos] = cn, out_q[pos] = co - 1;
+                    else if (cs == ST_I) out_r[pos] = UNV, out_q[pos] = co - 1;
+                    else out_r[pos] = cn, out_q[pos] = UNV;
+                    if (bn == g.start) break;
+                    cn = bn, co = bo, cs = bs;
+                }
+            }
+        }
+        res.n_pairs = cap - pos;
+        res.status = err;
+        return res;
+    }
+};
+
+// scratch sizing shared by host and device code
+struct ScratchDims {
+    uint32_t nbr, nbc, rw, f_max;
+    RP_HD ScratchDims(uint32_t V, uint32_t Q, uint32_t x, uint32_t o, uint32_t e) {
+        nbr = (V >> 3) + 1;
+        nbc = ((Q + 1) >> 3) + 1;
+        rw = (Q + 1 + 31) / 32 + 1;  // + 1: the per-row non-empty flag
+        uint32_t m = x > o + e ? x : o + e;
+        if (m == 0) m = 1;
+        f_max = (V + Q + 4) * m + o + 64;  // any score and any gap-cost heuristic value stays below this
+    }
+};
+
+}  // namespace replay
+}  // namespace poasta

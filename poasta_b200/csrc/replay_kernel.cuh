@@ -1,0 +1,168 @@
+// Device launcher for the order-exact search (replay_core.hpp). Included by align.cu.
+//
+// One warp = one in-flight alignment ("worker"). All 32 lanes zero the worker's scratch slab with
+// 128-bit stores, then lane 0 runs the (inherently sequential) state machine. Workers pull
+// alignments from a global counter, so a launch keeps every SM's warp slots busy until the batch
+// is drained. Results go to the same staging / scan / compact path as the DP traceback.
+#pragma once
+#include "replay_core.hpp"
+#include "search_index.hpp"
+
+namespace poasta {
+
+struct RGraphDesc {
+    uint32_t V, start, end;
+    uint32_t node_base;     // sym, dist_min, dist_max, is_exit
+    uint32_t succoff_base, predoff_base, buboff_base, pathoff_base;  // each V + 1 entries, values relative to *_base below
+    uint32_t succ_base, pred_base, bub_base, path_base;
+};
+
+struct ReplayDev {
+    const RGraphDesc *graphs;
+    const AlnDesc *alns;
+    const uint8_t *sym, *is_exit, *queries;
+    const uint32_t *dist_min, *dist_max, *succ_off, *succ, *pred_off, *pred, *bub_off, *bub, *path_off, *path_rem;
+    uint32_t n_alns;
+    replay::Params prm;
+    uint8_t *slabs;
+    uint64_t slab_bytes, off_cells, off_qhead, off_items, off_reached, off_dfa;  // byte offsets inside a slab (blk at 0)
+    uint32_t max_blocks, max_items;
+    uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
+    int32_t *status;
+    uint32_t *stats;  // per alignment: queued, visited, pruned, blocks
+};
+
+constexpr int REPLAY_WARPS_PER_CTA = 4;
+
+__global__ void __launch_bounds__(REPLAY_WARPS_PER_CTA * 32) replay_kernel(ReplayDev B) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t worker = blockIdx.x * REPLAY_WARPS_PER_CTA + (threadIdx.x >> 5);
+    uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
+    for (;;) {
+        uint32_t a = 0;
+        if (lane == 0) a = atomicAdd(B.counter, 1u);
+        a = __shfl_sync(0xFFFFFFFFu, a, 0);
+        if (a >= B.n_alns) break;
+        const AlnDesc ad = B.alns[a];
+        const RGraphDesc gd = B.graphs[ad.graph];
+        const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
+        // zero the block-pointer table, the bucket heads and the reached bitmaps (sizes of THIS alignment)
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 *p0 = reinterpret_cast<uint4 *>(slab);
+            const uint32_t n0 = ((uint64_t)dims.nbr * dims.nbc + 3) / 4;
+            for (uint32_t i = lane; i < n0; i += 32) p0[i] = z;
+            uint4 *p1 = reinterpret_cast<uint4 *>(slab + B.off_qhead);
+            const uint32_t n1 = ((uint64_t)dims.f_max * 3 + 3) / 4;
+            for (uint32_t i = lane; i < n1; i += 32) p1[i] = z;
+            uint4 *p2 = reinterpret_cast<uint4 *>(slab + B.off_reached);
+            const uint32_t n2 = ((uint64_t)gd.V * dims.rw + 3) / 4;
+            for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            replay::Graph g;
+            g.V = gd.V, g.start = gd.start, g.end = gd.end;
+            g.succ_off = B.succ_off + gd.succoff_base;
+            g.succ = B.succ + gd.succ_base;
+            g.pred_off = B.pred_off + gd.predoff_base;
+            g.pred = B.pred + gd.pred_base;
+            g.sym = B.sym + gd.node_base;
+            g.dist_min = B.dist_min + gd.node_base;
+            g.dist_max = B.dist_max + gd.node_base;
+            g.is_exit = B.is_exit + gd.node_base;
+            g.bub_off = B.bub_off + gd.buboff_base;
+            g.bub = B.bub + (uint64_t)gd.bub_base * 3;
+            g.path_off = B.path_off + gd.pathoff_base;
+            g.path_rem = B.path_rem + gd.path_base;
+            replay::Scratch s;
+            s.blk = reinterpret_cast<uint32_t *>(slab);
+            s.cells = reinterpret_cast<uint32_t *>(slab + B.off_cells);
+            s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
+            s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
+            s.reached = reinterpret_cast<uint32_t *>(slab + B.off_reached);
+            s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
+            s.nbc = dims.nbc, s.rw = dims.rw, s.f_max = dims.f_max;
+            s.max_blocks = B.max_blocks, s.max_items = B.max_items;
+            replay::Search search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
+            const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
+            B.scores[a] = r.score;
+            B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;
+            B.status[a] = r.status;
+            B.stats[4 * a + 0] = r.num_queued, B.stats[4 * a + 1] = r.num_visited, B.stats[4 * a + 2] = r.num_pruned;
+            B.stats[4 * a + 3] = search.n_blocks;
+        }
+        __syncwarp();
+    }
+}
+
+// Host-side packing of problems for the search kernel (node-id space + SearchIndex arrays).
+struct PackedReplay {
+    std::vector<RGraphDesc> graphs;
+    std::vector<AlnDesc> alns;
+    std::vector<uint8_t> sym, is_exit, queries;
+    std::vector<uint32_t> dist_min, dist_max, succ_off, succ, pred_off, pred, bub_off, bub, path_off, path_rem;
+    uint64_t out_elems = 0, total_cells = 0;
+    uint32_t max_V = 0, max_Q = 0;
+
+    void clear() {
+        graphs.clear(), alns.clear(), sym.clear(), is_exit.clear(), queries.clear();
+        dist_min.clear(), dist_max.clear(), succ_off.clear(), succ.clear(), pred_off.clear(), pred.clear();
+        bub_off.clear(), bub.clear(), path_off.clear(), path_rem.clear();
+        out_elems = total_cells = 0;
+        max_V = max_Q = 0;
+    }
+
+    uint32_t add_graph(const poasta_graph_view &v, const SearchIndex &si) {
+        RGraphDesc gd;
+        const uint32_t V = v.n_nodes;
+        gd.V = V, gd.start = v.start_node, gd.end = v.end_node;
+        gd.node_base = (uint32_t)sym.size();
+        gd.succoff_base = (uint32_t)succ_off.size();
+        gd.predoff_base = (uint32_t)pred_off.size();
+        gd.buboff_base = (uint32_t)bub_off.size();
+        gd.pathoff_base = (uint32_t)path_off.size();
+        gd.succ_base = (uint32_t)succ.size();
+        gd.pred_base = (uint32_t)pred.size();
+        gd.bub_base = (uint32_t)(bub.size() / 3);
+        gd.path_base = (uint32_t)path_rem.size();
+        sym.insert(sym.end(), v.symbol, v.symbol + V);
+        is_exit.insert(is_exit.end(), si.is_exit.begin(), si.is_exit.end());
+        dist_min.insert(dist_min.end(), si.dist_min.begin(), si.dist_min.end());
+        dist_max.insert(dist_max.end(), si.dist_max.begin(), si.dist_max.end());
+        succ_off.insert(succ_off.end(), v.succ_off, v.succ_off + V + 1);
+        succ.insert(succ.end(), v.succ, v.succ + v.succ_off[V]);
+        pred_off.insert(pred_off.end(), v.pred_off, v.pred_off + V + 1);
+        pred.insert(pred.end(), v.pred, v.pred + v.pred_off[V]);
+        bub_off.insert(bub_off.end(), si.bub_off.begin(), si.bub_off.end());
+        bub.insert(bub.end(), si.bub.begin(), si.bub.end());
+        if (si.path_off.empty()) {
+            path_off.insert(path_off.end(), V + 1, 0u);
+        } else {
+            path_off.insert(path_off.end(), si.path_off.begin(), si.path_off.end());
+            path_rem.insert(path_rem.end(), si.path_rem.begin(), si.path_rem.end());
+        }
+        max_V = std::max(max_V, V);
+        graphs.push_back(gd);
+        return (uint32_t)graphs.size() - 1;
+    }
+
+    void add_alignment(uint32_t graph, const uint8_t *q, uint32_t Q) {
+        AlnDesc a;
+        a.graph = graph;
+        a.Q = Q;
+        a.W = Q + 1;
+        a.query_base = (uint32_t)queries.size();
+        queries.insert(queries.end(), q, q + Q);
+        while (queries.size() & 3) queries.push_back(0);
+        a.trace_base = 0;
+        a.out_cap = graphs[graph].V + Q + 2;
+        a.out_base = (uint32_t)out_elems;
+        out_elems += a.out_cap;
+        total_cells += (uint64_t)(graphs[graph].V - 2) * Q;
+        max_Q = std::max(max_Q, Q);
+        alns.push_back(a);
+    }
+};
+
+}  // namespace poasta

@@ -30,7 +30,7 @@ class Unsupported(PoastaError):
 
 
 _BY_CODE = {-1: CudaError, -2: ValueError, -3: WeightsUnequalSize, -4: InvalidAlignment, -5: GraphError,
-            -6: NoAlignment, -7: Unsupported, -8: IOError}
+            -6: NoAlignment, -7: Unsupported, -8: IOError, -9: PoastaError}
 
 
 def check(code, what=""):

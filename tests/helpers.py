@@ -48,6 +48,8 @@ def oracle():
         o.oracle_msa_many.restype = C.c_double
         o.dpmodel_align.argtypes = [GV, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, u32p, u32p, C.c_uint32, u32p, u32p]
         o.dpmodel_align.restype = C.c_uint32
+        o.replay_host_align.argtypes = [GV, C.c_char_p, C.c_uint32] + [C.c_int] * 5 + [u32p, u32p, u32p, C.c_uint32, u32p,
+                                                                                    C.POINTER(C.c_uint64)]
         o.oracle_free.argtypes = [C.c_void_p]
         _oracle = o
     return _oracle
@@ -153,6 +155,20 @@ def oracle_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1, mock=False, prun
     flags = (1 if mock else 0) | (0 if pruning else 2)
     st = oracle().oracle_align(C.byref(cview), seq, len(seq), x, o, e, mode, heuristic, flags, C.byref(score),
                                r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), cap, C.byref(n), stats)
+    return st, score.value, pairs_from_arrays(r, q, n.value), list(stats)
+
+
+def replay_host_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1):
+    """Host build of the product's order-exact search core (test hook). Returns (status, score, pairs, stats)."""
+    seq = bytes(seq)
+    cview = _cview(view)
+    cap = cview.n_nodes + len(seq) + 8
+    r = np.zeros(cap, np.uint32)
+    q = np.zeros(cap, np.uint32)
+    score, n = C.c_uint32(), C.c_uint32()
+    stats = (C.c_uint64 * 5)()
+    st = oracle().replay_host_align(C.byref(cview), seq, len(seq), x, o, e, mode, heuristic, C.byref(score),
+                                    r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), cap, C.byref(n), stats)
     return st, score.value, pairs_from_arrays(r, q, n.value), list(stats)
 
 
