@@ -3,12 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--families F] [--impl ours|reference]
 
-One "step" = one progressive-MSA pass of the hot path over a batch of F families (19 alignment rounds,
-each one device batch), called through the public C-ABI entry `poasta_msa_batch` with HOST buffers.
-  value   GCUPS over the device kernels only (CUDA events around the fill/traceback launches, inputs of
-          each launch already resident in HBM) — explains the kernel;
+One "step" = one progressive-MSA pass of the hot path over one batch of F families (19 alignment rounds,
+each round one device batch), called through the public C-ABI entry `poasta_msa_batch` with HOST buffers.
+Step k aligns families [k*F, (k+1)*F): the default 5 steps x 2,000 families are BASELINE.json's config 2
+(10,000 families); warm-up steps use families beyond those.
+  value   GCUPS over the device kernels only (CUDA events on the launching stream around the DP fill /
+          traceback and the order-exact search launches; inputs of each launch resident in HBM);
   e2e     GCUPS of the whole call: FASTA text in host memory -> final graphs, including flattening,
           H2D/D2H copies and the host-side graph insertion between rounds — the headline.
+--tiebreak exact (default) returns the reference's alignments bit for bit (DP score + order-exact search);
+--tiebreak dp returns the optimal score and a co-optimal alignment from the DP traceback alone.
 1 CU = the three states (M, I, D) of one (real node, query position) pair; cells = sum V_real * Q
 (SURVEY.md §8d). Under torchrun each rank takes a disjoint shard of families (no collective on the
 data path; weak scaling: F families per GPU).
@@ -71,6 +75,7 @@ class ClockSampler:
 
 
 def make_families(first, count, args):
+    """Families [first, first + count) of config 2 (seeded per family, identical for both bench arms)."""
     from poasta_b200 import synth
     return [synth.config2_family(first + f, n_seqs=args.seqs, root_len=args.length, rate=args.rate) for f in range(count)]
 
@@ -95,13 +100,12 @@ def run_reference(args):
         return
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     cores = os.cpu_count() or 1
-    sample = max(8, min(args.families, 2 * cores))
-    fastas = make_families(0, sample, args)
-    for _ in range(args.warmup and 1):
-        cpu_reference(fastas[:max(1, min(cores, sample) // 4)], cores)
+    sample = max(8, min(args.families, 2 * cores))  # bounded sample of every step's batch (about 5-10 s of CPU work each)
+    for _ in range(1 if args.warmup else 0):
+        cpu_reference(make_families(args.steps * args.families, max(1, cores // 2), args), cores)
     tot_s = tot_cells = tot_seqs = 0
-    for _ in range(args.steps):
-        s, c, q = cpu_reference(fastas, cores)
+    for k in range(args.steps):
+        s, c, q = cpu_reference(make_families(k * args.families, sample, args), cores)
         tot_s += s
         tot_cells += c
         tot_seqs += q
@@ -111,28 +115,32 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "seqs_per_s": tot_seqs / tot_s,
-        "config": workload_config(args, sample),
+        "config": workload_config(args, args.families),
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {args.families} families per step, one family per task, {cores} threads; "
+                         "sample": f"first {sample} of the {args.families} families of every step, one family per task, {cores} threads; "
                                    "equivalent GCUPS (A* visits a fraction of the cells)"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, families):
-    return {"workload": f"config2: {families} synthetic gene families x {args.seqs} seqs x {args.length} bp, "
-                        f"{args.rate:.0%} subs+indels, global, costs 4/6/2, progressive MSA ({args.seqs - 1} rounds)",
-            "families_per_gpu": families, "l2": "inputs larger than L2 (trace store >> 126 MB per round)"}
+def workload_config(args, families, world=1):
+    total = families * args.steps * world
+    return {"workload": f"config2: {total} synthetic gene families x {args.seqs} seqs x {args.length} bp, "
+                        f"{args.rate:.0%} subs+indels, global, costs 4/6/2, mingap; progressive MSA ({args.seqs - 1} rounds) in "
+                        f"{args.steps} steps of {families} families per GPU",
+            "families_per_step_per_gpu": families, "tiebreak": getattr(args, "tiebreak", "exact"),
+            "l2": "every step reads different families; per-round working set (tables, trace) is far larger than the 126 MB L2"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "10000")))
+    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "2000")), help="families per step per GPU")
+    ap.add_argument("--tiebreak", default=os.environ.get("BENCH_TIEBREAK", "exact"), choices=["exact", "dp"])
     ap.add_argument("--seqs", type=int, default=20)
     ap.add_argument("--length", type=int, default=1000)
     ap.add_argument("--rate", type=float, default=0.05)
@@ -160,21 +168,26 @@ def main():
         dist.barrier()
     from poasta_b200 import aligner, msa_batch
 
-    fastas = make_families(rank * args.families, args.families, args)
-    warm = fastas[:max(64, args.families // 20)]
+    from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT
+    tiebreak = TIEBREAK_DP if args.tiebreak == "dp" else TIEBREAK_EXACT
+    F = args.families
+    # step k of rank r aligns families [(k * world + r) * F, ...); warm-up batches lie beyond the timed ones
+    batches = [make_families((k * world + rank) * F, F, args) for k in range(args.steps)]
+    warm_batches = [make_families(((args.steps + w) * world + rank) * F, F, args) for w in range(min(args.warmup, 2))]
 
     def step(batch):
         t0 = time.perf_counter()
-        graphs, scores, cells = msa_batch(batch, device=local)
+        graphs, scores, cells = msa_batch(batch, device=local, tiebreak=tiebreak)
         wall = time.perf_counter() - t0
         kms, launches, _ = aligner.last_batch_stats()
+        sms = aligner.last_batch_search_ms()
         h2d, d2h = aligner.last_batch_io()
         nseq = sum(len(s) for s in scores)
         del graphs
-        return wall, kms, launches, cells, nseq, h2d, d2h
+        return [wall, kms, sms, launches, cells, nseq, h2d, d2h]
 
     for w in range(args.warmup):
-        step(warm if w < args.warmup - 1 else fastas[:max(64, args.families // 4)])
+        step(warm_batches[w % len(warm_batches)])
 
     def sync():
         torch.cuda.synchronize()
@@ -186,53 +199,58 @@ def main():
         sampler.start()
     sync()
     t_begin = time.perf_counter()
-    tot = [0.0, 0.0, 0, 0, 0, 0, 0]
-    for _ in range(args.steps):
-        r = step(fastas)
-        tot = [a + b for a, b in zip(tot, r)]
+    tot = [0.0] * 8
+    for k in range(args.steps):
+        tot = [a_ + b_ for a_, b_ in zip(tot, step(batches[k]))]
     sync()
     wall = time.perf_counter() - t_begin
     clocks = sampler.stop() if rank == 0 else None
 
-    wall_t = torch.tensor([wall, tot[1]], dtype=torch.float64, device="cuda")
-    sums = torch.tensor([tot[3], tot[4], tot[2], tot[5], tot[6]], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([wall, tot[1], tot[2], tot[1] + tot[2]], dtype=torch.float64, device="cuda")
+    sums = torch.tensor(tot[3:], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    wall_max, kms_max = wall_t.tolist()
-    cells, nseq, launches, h2d, d2h = sums.tolist()
+    wall_max, dp_ms, search_ms, dev_ms = mx.tolist()
+    launches, cells, nseq, h2d, d2h = sums.tolist()
 
     if rank == 0:
         peak, which = peaks()
-        gcups_dev = cells / (kms_max / 1e3) / 1e9
+        gcups_dev = cells / (dev_ms / 1e3) / 1e9
         gcups_e2e = cells / wall_max / 1e9
-        # roofline of the dominant kernel (dp_fill): algorithmic bytes = 1 B per cell update
         per_rank_cells = cells / world
-        achieved = per_rank_cells * ALG_BYTES_PER_CU / (kms_max / 1e3) / 1e9
+        # roofline of the dominant kernel of the step (by device time)
+        dominant = "replay_kernel (order-exact search)" if search_ms > dp_ms else "dp_fill_kernel"
+        dom_ms = max(search_ms, dp_ms)
+        achieved = per_rank_cells * ALG_BYTES_PER_CU / (dom_ms / 1e3) / 1e9
+        dp_gbs = per_rank_cells * ALG_BYTES_PER_CU / (dp_ms / 1e3) / 1e9 if dp_ms else None
         line = {
             "metric": "GCUPS", "value": gcups_dev, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s32", "data": "synthetic",
-            "config": workload_config(args, args.families),
-            "seqs_per_s": nseq / wall_max, "kernel_ms_per_step": kms_max / args.steps,
+            "config": workload_config(args, F, world),
+            "seqs_per_s": nseq / wall_max,
+            "device_ms_per_step": {"dp_fill+traceback": dp_ms / args.steps, "order_exact_search": search_ms / args.steps},
             "e2e": {"value": gcups_e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d / world / args.steps,
                     "d2h_bytes_per_step": d2h / world / args.steps, "seqs_per_s": nseq / wall_max},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which,
-                         "note": "algorithmic bytes = 1 B/CU (traceback budget); int-op view: "
-                                 f"{per_rank_cells * ALG_INT_OPS_PER_CU / (kms_max / 1e3) / 1e12:.3f} Tint-op/s at 12 ops/CU"},
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "note": "algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) x cells of the step / "
+                                 "kernel time (CUDA events). dp_fill_kernel alone: "
+                                 + (f"{dp_gbs:.1f} GB/s = {dp_gbs / peak:.4f} of peak, "
+                                    f"{per_rank_cells * ALG_INT_OPS_PER_CU / (dp_ms / 1e3) / 1e12:.3f} Tint-op/s at 12 ops/CU" if dp_ms else "n/a")},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
             cores = os.cpu_count() or 1
-            sample = max(4, min(args.families, cores))
-            s, c, q = cpu_reference(fastas[:sample], cores)
-            line["cpu_baseline"] = {"value": c / s / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} families of the step, one family per task, {cores} threads, "
-                                              f"{s:.1f} s wall; equivalent GCUPS (A* visits a fraction of the cells)",
-                                    "seqs_per_s": q / s}
+            sample = max(4, min(F, cores))
+            s_, c_, q_ = cpu_reference(batches[0][:sample], cores)
+            line["cpu_baseline"] = {"value": c_ / s_ / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} families of step 0, one family per task, {cores} threads, "
+                                              f"{s_:.1f} s wall; equivalent GCUPS (A* visits a fraction of the cells)",
+                                    "seqs_per_s": q_ / s_}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
