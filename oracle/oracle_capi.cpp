@@ -290,14 +290,13 @@ uint32_t dpmodel_align(const poasta_graph_view *view, const uint8_t *seq, uint32
 // logic that runs on the device. TEST HOOK ONLY: the product never executes this path (it has no CPU fallback).
 int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, int mode,
                       int heuristic, uint32_t *score, uint32_t *rpos, uint32_t *qpos, uint32_t cap, uint32_t *n_pairs,
-                      uint64_t *stats) {
+                      uint64_t *stats, int cell16) {
     namespace rp = poasta::replay;
     using rp::Item;
     using rp::Params;
     using rp::Result;
     using rp::Scratch;
     using rp::ScratchDims;
-    using rp::Search;
     poasta::SearchIndex si;
     si.build(*view, heuristic == 2);
     rp::Graph g{view->n_nodes, view->start_node, view->end_node, view->succ_off, view->succ, view->pred_off, view->pred,
@@ -312,17 +311,26 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     Scratch s{blk.data(), (uint32_t *)cells.data(), qhead.data(), items.data(), reached.data(), dfa.data(),
               d.nbc, d.rw, max_blocks, max_items, d.f_max};
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
-    Search search(g, seq, qlen, p, s);
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
-    Result r = search.run(out_r.data(), out_q.data(), ocap);
+    Result r;
+    uint32_t used_blocks = 0, used_items = 0;
+    if (cell16) {
+        rp::Search<uint16_t> search(g, seq, qlen, p, s);
+        r = search.run(out_r.data(), out_q.data(), ocap);
+        used_blocks = search.n_blocks, used_items = search.n_items;
+    } else {
+        rp::Search<uint32_t> search(g, seq, qlen, p, s);
+        r = search.run(out_r.data(), out_q.data(), ocap);
+        used_blocks = search.n_blocks, used_items = search.n_items;
+    }
     *score = r.score;
     *n_pairs = r.n_pairs;
     for (uint32_t i = 0; i < r.n_pairs && i < cap; ++i) {
         rpos[i] = out_r[ocap - r.n_pairs + i];
         qpos[i] = out_q[ocap - r.n_pairs + i];
     }
-    if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = search.n_blocks, stats[4] = search.n_items;
+    if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = used_blocks, stats[4] = used_items;
     return r.status;
 }
 

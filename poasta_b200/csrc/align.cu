@@ -655,7 +655,7 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
 
 // ---- order-exact search path ------------------------------------------------------------------------
 static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_params &prm, ChunkResult &res,
-                      std::vector<uint32_t> *stats_out) {
+                      std::vector<uint32_t> *stats_out, bool full_arenas) {
     const uint32_t n = (uint32_t)pr.alns.size();
     if (n == 0) return 0;
     CK(cudaSetDevice(c.device));
@@ -663,15 +663,21 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     auto up = [](uint64_t b) { return (b + 255) & ~(uint64_t)255; };
     const uint64_t blk_entries = (uint64_t)dmax.nbr * dmax.nbc;
     const uint64_t cells_per_aln = (uint64_t)pr.max_V * (pr.max_Q + 1);
-    uint64_t max_blocks = blk_entries;
-    uint64_t max_items = 262144 + cells_per_aln / 8;
+    // u16 score cells when no reachable score can hit 0xFFFF (all nodes deleted + all query bases inserted is the worst case)
+    const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
+                           prm.gap_open;
+    const bool cell16 = worst < 0xFF00u;
+    const uint64_t block_bytes = cell16 ? 384 : 768;
+    // the search touches a band of the table: size the per-worker arenas for that and retry the rare overflow at full size
+    uint64_t max_blocks = full_arenas ? blk_entries : std::min<uint64_t>(blk_entries, std::max<uint64_t>(4096, blk_entries * 9 / 20));
+    uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 131072 + cells_per_aln / 16;
     uint64_t off_cells = up(blk_entries * 4);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, std::min<uint64_t>((uint64_t)64 << 30, total_b / 3));
+    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, std::min<uint64_t>((uint64_t)96 << 30, total_b / 2));
     uint64_t slab = 0, off_qhead = 0, off_items = 0, off_reached = 0, off_dfa = 0;
     auto layout = [&]() {
-        off_qhead = off_cells + up(max_blocks * 768);
+        off_qhead = off_cells + up(max_blocks * block_bytes);
         off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
         off_reached = off_items + up(max_items * 16);
         off_dfa = off_reached + up((uint64_t)pr.max_V * dmax.rw * 4);
@@ -680,19 +686,20 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     layout();
     // keep at least 2 workers per SM resident: shrink the cell arena (the search touches a band of the table) before
     // shrinking the worker count; exhausted arenas are reported per alignment (RP_OUT_OF_BLOCKS) and retried at full size
-    const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 32);
-    if (slab * want_workers > budget && max_blocks > 4096) {
-        const uint64_t fixed = slab - up(max_blocks * 768);
+    const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
+    if (!full_arenas && slab * want_workers > budget && max_blocks > 4096) {
+        const uint64_t fixed = slab - up(max_blocks * block_bytes);
         const uint64_t per = budget / want_workers;
-        uint64_t nb = per > fixed ? (per - fixed) / 768 : 0;
+        uint64_t nb = per > fixed ? (per - fixed) / block_bytes : 0;
         nb = std::max<uint64_t>(nb, std::min<uint64_t>(blk_entries, std::max<uint64_t>(4096, blk_entries / 4)));
         max_blocks = std::min(max_blocks, nb);
         layout();
     }
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
-    workers = ((workers + REPLAY_WARPS_PER_CTA - 1) / REPLAY_WARPS_PER_CTA) * REPLAY_WARPS_PER_CTA;
+    const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 32 ? 2 : 1;  // at most 32 CTAs are resident per SM
+    workers = ((workers + warps_per_cta - 1) / warps_per_cta) * warps_per_cta;
     if (!c.r_slabs.reserve(workers * slab)) {
-        workers = REPLAY_WARPS_PER_CTA;
+        workers = warps_per_cta;
         if (!c.r_slabs.reserve(workers * slab)) return POASTA_ERR_CUDA;
     }
     bool ok = c.r_graphs.reserve(pr.graphs.size() * sizeof(RGraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
@@ -763,7 +770,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     P.alns = B.alns, P.n_alns = n, P.out_r = B.out_r, P.out_q = B.out_q, P.n_pairs = B.n_pairs;
 
     CK(cudaEventRecord(c.ev0, s));
-    replay_kernel<<<(unsigned)(workers / REPLAY_WARPS_PER_CTA), REPLAY_WARPS_PER_CTA * 32, 0, s>>>(B);
+    if (cell16) replay_kernel<uint16_t><<<(unsigned)(workers / warps_per_cta), warps_per_cta * 32, 0, s>>>(B);
+    else replay_kernel<uint32_t><<<(unsigned)(workers / warps_per_cta), warps_per_cta * 32, 0, s>>>(B);
     scan_kernel<<<1, 1024, 0, s>>>(B.n_pairs, (uint32_t *)c.offsets.d, n);
     CK(cudaEventRecord(c.ev1, s));
     CK(cudaGetLastError());
@@ -818,38 +826,54 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
     DeviceContext &c = ctx_for(device);
     int rc = c.init(device);
     if (rc) return rc;
+    struct Out {
+        uint32_t score = 0;
+        int32_t status = 0;
+        std::vector<uint32_t> r, q;
+    };
+    std::vector<Out> outs(probs.size());
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < probs.size(); ++i) {
+        if (probs[i].graph->n_nodes <= 2) outs[i].score = probs[i].qlen * 4u;  // empty-graph shortcut (aligner/mod.rs:124-142)
+        else todo.push_back(i);
+    }
     PackedReplay pr;
     ChunkResult res;
-    std::vector<size_t> idx;
     SearchIndex tmp;
-    uint32_t last_key = 0xFFFFFFFFu, last_gid = 0;
-    for (size_t i = 0; i < probs.size(); ++i) {
-        const Problem &p = probs[i];
-        if (p.graph->n_nodes <= 2) continue;  // empty-graph shortcut handled below (aligner/mod.rs:124-142)
-        if (p.graph_key != last_key || pr.graphs.empty()) {
-            const SearchIndex *si = p.sidx;
-            if (!si) {
-                tmp.build(*p.graph, prm.heuristic == 2);
-                si = &tmp;
+    for (int attempt = 0; attempt < 2 && !todo.empty(); ++attempt) {
+        pr.clear();
+        uint32_t last_key = 0xFFFFFFFFu, last_gid = 0;
+        for (size_t i : todo) {
+            const Problem &p = probs[i];
+            if (p.graph_key != last_key || pr.graphs.empty()) {
+                const SearchIndex *si = p.sidx;
+                if (!si) {
+                    tmp.build(*p.graph, prm.heuristic == 2);
+                    si = &tmp;
+                }
+                last_gid = pr.add_graph(*p.graph, *si);
+                last_key = p.graph_key;
             }
-            last_gid = pr.add_graph(*p.graph, *si);
-            last_key = p.graph_key;
+            pr.add_alignment(last_gid, p.query, p.qlen);
         }
-        pr.add_alignment(last_gid, p.query, p.qlen);
-        idx.push_back(i);
-    }
-    rc = run_replay(c, pr, prm, res, nullptr);
-    if (rc) return rc;
-    size_t k = 0;
-    for (size_t i = 0; i < probs.size(); ++i) {
-        if (probs[i].graph->n_nodes <= 2) {
-            sink(i, probs[i].qlen * 4u, 0, (const uint32_t *)nullptr, (const uint32_t *)nullptr, 0u);
-            continue;
+        rc = run_replay(c, pr, prm, res, nullptr, attempt == 1);
+        if (rc) return rc;
+        std::vector<size_t> again;
+        for (size_t k = 0; k < todo.size(); ++k) {
+            const int st = res.status[k];
+            if (attempt == 0 && (st == replay::RP_OUT_OF_BLOCKS || st == replay::RP_OUT_OF_ITEMS)) {
+                again.push_back(todo[k]);  // arena sized for the common case was too small: rerun with full-size arenas
+                continue;
+            }
+            Out &o = outs[todo[k]];
+            o.score = res.scores[k];
+            o.status = map_replay_status(st);
+            o.r.assign(res.dense_r + res.offsets[k], res.dense_r + res.offsets[k] + res.n_pairs[k]);
+            o.q.assign(res.dense_q + res.offsets[k], res.dense_q + res.offsets[k] + res.n_pairs[k]);
         }
-        sink(i, res.scores[k], (int32_t)map_replay_status(res.status[k]), res.dense_r + res.offsets[k], res.dense_q + res.offsets[k],
-             res.n_pairs[k]);
-        ++k;
+        todo.swap(again);
     }
+    for (size_t i = 0; i < probs.size(); ++i) sink(i, outs[i].score, outs[i].status, outs[i].r.data(), outs[i].q.data(), (uint32_t)outs[i].r.size());
     return 0;
 }
 

@@ -58,12 +58,12 @@ struct Item {
 
 struct Scratch {  // one slab per in-flight alignment
     uint32_t *blk;       // block pointer table, nbr * nbc entries (0 = not allocated, else block index + 1)
-    uint32_t *cells;     // max_blocks * 192 u32
+    void *cells;         // max_blocks * 192 scores (u16 when every reachable score fits, else u32)
     uint32_t *qhead;     // f_max * 3 stack heads (0 = empty, else item index + 1)
     Item *items;         // max_items
     uint32_t *reached;   // V * rw bitmap words
     uint32_t *dfa;       // (V + 2) * 3
-    uint32_t nbc, rw, max_blocks, max_items, f_max;  // rw = row stride in words; word rw-1 of a row is its non-empty flag
+    uint32_t nbc, rw, max_blocks, max_items, f_max;  // rw = row stride in words: bitmap words, then lo, then hi + 1 (0 = empty)
 };
 
 struct Params {
@@ -79,7 +79,11 @@ struct Result {
     uint32_t num_queued, num_visited, num_pruned;
 };
 
+// CellT = uint16_t halves the table footprint (more alignments in flight); the host picks it only when the largest
+// possible score (every node deleted + every query base inserted) is below 0xFFFF.
+template <typename CellT>
 struct Search {
+    static constexpr CellT CUNV = (CellT)~(CellT)0;
     const Graph &g;
     const uint8_t *q;
     const uint32_t Q;
@@ -95,7 +99,7 @@ struct Search {
     RP_HD bool sym_eq(uint32_t node, uint8_t c) const { return node == g.end || g.sym[node] == c; }
 
     // ---- visited table -------------------------------------------------------------------------
-    RP_HD uint32_t *cell(uint32_t node, uint32_t off, bool create) {
+    RP_HD CellT *cell(uint32_t node, uint32_t off, bool create) {
         uint32_t *bp = s.blk + (size_t)(node >> 3) * s.nbc + (off >> 3);
         uint32_t b = *bp;
         if (b == 0) {
@@ -104,26 +108,33 @@ struct Search {
                 err = RP_OUT_OF_BLOCKS;
                 return nullptr;
             }
-            uint4 *c = reinterpret_cast<uint4 *>(s.cells + (size_t)n_blocks * 192);
-            for (int i = 0; i < 48; ++i) c[i] = uint4{UNV, UNV, UNV, UNV};
+            uint4 *c = reinterpret_cast<uint4 *>(static_cast<CellT *>(s.cells) + (size_t)n_blocks * 192);
+            for (int i = 0; i < (int)(12 * sizeof(CellT)); ++i) c[i] = uint4{UNV, UNV, UNV, UNV};
             b = ++n_blocks;
             *bp = b;
         }
-        return s.cells + (size_t)(b - 1) * 192 + ((node & 7) * 8 + (off & 7)) * 3;
+        return static_cast<CellT *>(s.cells) + (size_t)(b - 1) * 192 + ((node & 7) * 8 + (off & 7)) * 3;
     }
     RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) {
-        const uint32_t *c = cell(node, off, false);
-        return c ? c[st] : UNV;
+        const CellT *c = cell(node, off, false);
+        if (!c) return UNV;
+        const CellT v = c[st];
+        return v == CUNV ? UNV : (uint32_t)v;
     }
     RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
-        uint32_t *c = cell(node, off, true);
-        if (c) c[st] = v;
+        CellT *c = cell(node, off, true);
+        if (c) c[st] = (CellT)v;
     }
     RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
-        uint32_t *c = cell(node, off, true);
+        CellT *c = cell(node, off, true);
         if (!c) return false;
-        if (v < c[st]) {
-            c[st] = v;
+        if (sizeof(CellT) == 2 && v >= 0xFFFFu) {  // cannot happen when the host sized CellT correctly
+            err = RP_SCORE_WRAP;
+            return false;
+        }
+        const CellT cur = c[st];
+        if (cur == CUNV || v < (uint32_t)cur) {
+            c[st] = (CellT)v;
             return true;
         }
         return false;
@@ -223,47 +234,60 @@ struct Search {
     }
 
     // ---- reached sets (BTreeSet<offset> per exit) --------------------------------------------------------
+    // Row = bitmap words followed by [lo, hi + 1] of the members so range queries never scan outside the occupied band.
     RP_HD void mark_reached(uint32_t node, uint32_t off, uint32_t st) {
         if (st == ST_M && g.is_exit[node]) {
             uint32_t *row = s.reached + (size_t)node * s.rw;
             row[off >> 5] |= 1u << (off & 31);
-            row[s.rw - 1] = 1;
+            uint32_t *b = row + (s.rw - 2);
+            if (b[1] == 0) {
+                b[0] = off, b[1] = off + 1;
+            } else {
+                if (off < b[0]) b[0] = off;
+                if (off + 1 > b[1]) b[1] = off + 1;
+            }
         }
+    }
+    RP_HD static uint32_t hi_bit(uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+        return 31 - __clz(bits);
+#else
+        return 31 - __builtin_clz(bits);
+#endif
+    }
+    RP_HD static uint32_t lo_bit(uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+        return __ffs(bits) - 1;
+#else
+        return __builtin_ctz(bits);
+#endif
     }
     // largest member < lim, or UNV
     RP_HD uint32_t reached_prev(const uint32_t *row, uint32_t lim) const {
-        if (lim == 0) return UNV;
-        uint32_t i = lim - 1;
-        if ((i >> 5) >= s.rw - 1) i = (s.rw - 1) * 32 - 1;
-        int w = (int)(i >> 5);
+        const uint32_t lo = row[s.rw - 2], hi1 = row[s.rw - 1];
+        if (hi1 == 0 || lim <= lo) return UNV;
+        const uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
+        uint32_t w = i >> 5;
+        const uint32_t wlo = lo >> 5;
         uint32_t bits = row[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
         for (;;) {
-            if (bits) {
-#if defined(__CUDA_ARCH__)
-                return (uint32_t)w * 32 + (31 - __clz(bits));
-#else
-                return (uint32_t)w * 32 + (31 - __builtin_clz(bits));
-#endif
-            }
-            if (--w < 0) return UNV;
-            bits = row[w];
+            if (bits) return w * 32 + hi_bit(bits);
+            if (w == wlo) return UNV;
+            bits = row[--w];
         }
     }
     // smallest member >= lim, or UNV
     RP_HD uint32_t reached_next(const uint32_t *row, uint32_t lim) const {
-        uint32_t w = lim >> 5;
-        if (w >= s.rw - 1) return UNV;
-        uint32_t bits = row[w] & (0xFFFFFFFFu << (lim & 31));
+        const uint32_t lo = row[s.rw - 2], hi1 = row[s.rw - 1];
+        if (hi1 == 0 || lim >= hi1) return UNV;
+        const uint32_t i = lim < lo ? lo : lim;
+        uint32_t w = i >> 5;
+        const uint32_t whi = (hi1 - 1) >> 5;
+        uint32_t bits = row[w] & (0xFFFFFFFFu << (i & 31));
         for (;;) {
-            if (bits) {
-#if defined(__CUDA_ARCH__)
-                return w * 32 + (__ffs(bits) - 1);
-#else
-                return w * 32 + __builtin_ctz(bits);
-#endif
-            }
-            if (++w >= s.rw - 1) return UNV;
-            bits = row[w];
+            if (bits) return w * 32 + lo_bit(bits);
+            if (w == whi) return UNV;
+            bits = row[++w];
         }
     }
 
@@ -595,7 +619,7 @@ struct ScratchDims {
     RP_HD ScratchDims(uint32_t V, uint32_t Q, uint32_t x, uint32_t o, uint32_t e) {
         nbr = (V >> 3) + 1;
         nbc = ((Q + 1) >> 3) + 1;
-        rw = (Q + 1 + 31) / 32 + 1;  // + 1: the per-row non-empty flag
+        rw = (Q + 1 + 31) / 32 + 2;  // + 2: [lo, hi + 1] of the row's members
         uint32_t m = x > o + e ? x : o + e;
         if (m == 0) m = 1;
         f_max = (V + Q + 4) * m + o + 64;  // any score and any gap-cost heuristic value stays below this

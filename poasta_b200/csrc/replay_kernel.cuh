@@ -32,11 +32,12 @@ struct ReplayDev {
     uint32_t *stats;  // per alignment: queued, visited, pruned, blocks
 };
 
-constexpr int REPLAY_WARPS_PER_CTA = 4;
+constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few workers over all SMs; 2 reaches 64 warps/SM
 
-__global__ void __launch_bounds__(REPLAY_WARPS_PER_CTA * 32) replay_kernel(ReplayDev B) {
+template <typename CellT>
+__global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32) replay_kernel(ReplayDev B) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t worker = blockIdx.x * REPLAY_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
     for (;;) {
         uint32_t a = 0;
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(REPLAY_WARPS_PER_CTA * 32) replay_kernel(Repla
             g.path_rem = B.path_rem + gd.path_base;
             replay::Scratch s;
             s.blk = reinterpret_cast<uint32_t *>(slab);
-            s.cells = reinterpret_cast<uint32_t *>(slab + B.off_cells);
+            s.cells = slab + B.off_cells;
             s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
             s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
             s.reached = reinterpret_cast<uint32_t *>(slab + B.off_reached);
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
             s.nbc = dims.nbc, s.rw = dims.rw, s.f_max = dims.f_max;
             s.max_blocks = B.max_blocks, s.max_items = B.max_items;
-            replay::Search search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
+            replay::Search<CellT> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;

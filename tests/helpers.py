@@ -49,7 +49,7 @@ def oracle():
         o.dpmodel_align.argtypes = [GV, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, u32p, u32p, C.c_uint32, u32p, u32p]
         o.dpmodel_align.restype = C.c_uint32
         o.replay_host_align.argtypes = [GV, C.c_char_p, C.c_uint32] + [C.c_int] * 5 + [u32p, u32p, u32p, C.c_uint32, u32p,
-                                                                                    C.POINTER(C.c_uint64)]
+                                                                                    C.POINTER(C.c_uint64), C.c_int]
         o.oracle_free.argtypes = [C.c_void_p]
         _oracle = o
     return _oracle
@@ -158,7 +158,7 @@ def oracle_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1, mock=False, prun
     return st, score.value, pairs_from_arrays(r, q, n.value), list(stats)
 
 
-def replay_host_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1):
+def replay_host_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1, cell16=False):
     """Host build of the product's order-exact search core (test hook). Returns (status, score, pairs, stats)."""
     seq = bytes(seq)
     cview = _cview(view)
@@ -168,7 +168,7 @@ def replay_host_align(view, seq, x=4, o=6, e=2, mode=0, heuristic=1):
     score, n = C.c_uint32(), C.c_uint32()
     stats = (C.c_uint64 * 5)()
     st = oracle().replay_host_align(C.byref(cview), seq, len(seq), x, o, e, mode, heuristic, C.byref(score),
-                                    r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), cap, C.byref(n), stats)
+                                    r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), cap, C.byref(n), stats, 1 if cell16 else 0)
     return st, score.value, pairs_from_arrays(r, q, n.value), list(stats)
 
 

@@ -23,8 +23,9 @@ def test_search_core_equals_oracle_on_families(heuristic):
     n = 0
     for f in range(3):
         for g, seq, st, sc, pairs, stats in _cases(synth.config2_family(f, n_seqs=8, root_len=250, rate=0.06), heuristic):
-            st2, sc2, pairs2, stats2 = H.replay_host_align(g, seq, heuristic=heuristic)
-            assert (st2, sc2, pairs2, stats2[:3]) == (st, sc, pairs, stats[:3])
+            for cell16 in (False, True):  # u32 and u16 score cells
+                st2, sc2, pairs2, stats2 = H.replay_host_align(g, seq, heuristic=heuristic, cell16=cell16)
+                assert (st2, sc2, pairs2, stats2[:3]) == (st, sc, pairs, stats[:3])
             n += 1
     assert n == 21
 
