@@ -701,7 +701,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         layout();
     }
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
-    const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 32 ? 2 : 1;  // at most 32 CTAs are resident per SM
+    const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
     workers = ((workers + warps_per_cta - 1) / warps_per_cta) * warps_per_cta;
     if (!c.r_slabs.reserve(workers * slab)) {
         workers = warps_per_cta;
@@ -775,8 +775,19 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     P.alns = B.alns, P.n_alns = n, P.out_r = B.out_r, P.out_q = B.out_q, P.n_pairs = B.n_pairs;
 
     CK(cudaEventRecord(c.ev0, s));
-    if (cell16) replay_kernel<uint16_t><<<(unsigned)(workers / warps_per_cta), warps_per_cta * 32, 0, s>>>(B);
-    else replay_kernel<uint32_t><<<(unsigned)(workers / warps_per_cta), warps_per_cta * 32, 0, s>>>(B);
+    {
+        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 24;
+        const dim3 grid((unsigned)(workers / warps_per_cta)), block(warps_per_cta * 32);
+        if (cell16) {
+            if (minb >= 32) replay_kernel<uint16_t, 32><<<grid, block, 0, s>>>(B);
+            else if (minb >= 24) replay_kernel<uint16_t, 24><<<grid, block, 0, s>>>(B);
+            else replay_kernel<uint16_t, 14><<<grid, block, 0, s>>>(B);
+        } else {
+            if (minb >= 32) replay_kernel<uint32_t, 32><<<grid, block, 0, s>>>(B);
+            else if (minb >= 24) replay_kernel<uint32_t, 24><<<grid, block, 0, s>>>(B);
+            else replay_kernel<uint32_t, 14><<<grid, block, 0, s>>>(B);
+        }
+    }
     scan_kernel<<<1, 1024, 0, s>>>(B.n_pairs, (uint32_t *)c.offsets.d, n);
     CK(cudaEventRecord(c.ev1, s));
     CK(cudaGetLastError());

@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define RP_HD __host__ __device__ __forceinline__
+#define RP_NI __host__ __device__ __forceinline__
 #else
 #define RP_HD inline
+#define RP_NI inline
 struct alignas(16) uint4 {
     uint32_t x, y, z, w;
 };
@@ -99,7 +101,7 @@ struct Search {
     RP_HD bool sym_eq(uint32_t node, uint8_t c) const { return node == g.end || g.sym[node] == c; }
 
     // ---- visited table -------------------------------------------------------------------------
-    RP_HD CellT *cell(uint32_t node, uint32_t off, bool create) {
+    RP_NI CellT *cell(uint32_t node, uint32_t off, bool create) {
         uint32_t *bp = s.blk + (size_t)(node >> 3) * s.nbc + (off >> 3);
         uint32_t b = *bp;
         if (b == 0) {
@@ -292,7 +294,7 @@ struct Search {
     }
 
     // reached.rs:191-255
-    RP_HD bool can_improve_at(uint32_t exit, uint32_t off, uint32_t score, uint32_t left, uint32_t right, uint32_t min_dist_to_end) {
+    RP_NI bool can_improve_at(uint32_t exit, uint32_t off, uint32_t score, uint32_t left, uint32_t right, uint32_t min_dist_to_end) {
         uint32_t implicit;
         if (left != UNV && right != UNV) {
             const uint32_t il = add(get(exit, left, ST_M), gap_cost(ST_M, off - left));
@@ -313,7 +315,7 @@ struct Search {
     }
 
     // reached.rs:38-189
-    RP_HD bool can_improve_bubble(uint32_t exit, uint32_t min_d, uint32_t max_d, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+    RP_NI bool can_improve_bubble(uint32_t exit, uint32_t min_d, uint32_t max_d, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
         const uint32_t *row = s.reached + (size_t)exit * s.rw;
         // is_empty(): any reached offset at this exit
         if (row[s.rw - 1] == 0) return true;
@@ -363,7 +365,7 @@ struct Search {
     }
 
     // ---- backtrace (gap_affine.rs:550-657) ------------------------------------------------------------------
-    RP_HD bool bt(uint32_t node, uint32_t off, uint32_t st, uint32_t &bn, uint32_t &bo, uint32_t &bs) {
+    RP_NI bool bt(uint32_t node, uint32_t off, uint32_t st, uint32_t &bn, uint32_t &bo, uint32_t &bs) {
         const uint32_t cur = get(node, off, st);
         if (cur == UNV) return false;
         if (st == ST_M) {

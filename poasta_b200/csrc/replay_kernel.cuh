@@ -34,8 +34,10 @@ struct ReplayDev {
 
 constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few workers over all SMs; 2 reaches 64 warps/SM
 
-template <typename CellT>
-__global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32) replay_kernel(ReplayDev B) {
+// MINB = minimum resident CTAs per SM the register allocation must allow. Only lane 0 of a warp runs the state machine
+// but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
+template <typename CellT, int MINB>
+__global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
