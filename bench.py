@@ -172,8 +172,9 @@ def main():
     tiebreak = TIEBREAK_DP if args.tiebreak == "dp" else TIEBREAK_EXACT
     F = args.families
     # step k of rank r aligns families [(k * world + r) * F, ...); warm-up batches lie beyond the timed ones
-    batches = [make_families((k * world + rank) * F, F, args) for k in range(args.steps)]
-    warm_batches = [make_families(((args.steps + w) * world + rank) * F, F, args) for w in range(min(args.warmup, 2))]
+    from poasta_b200.sharding import step_family_range
+    batches = [make_families(step_family_range(k, rank, world, F)[0], F, args) for k in range(args.steps)]
+    warm_batches = [make_families(step_family_range(args.steps + w, rank, world, F)[0], F, args) for w in range(min(args.warmup, 2))]
 
     def step(batch):
         t0 = time.perf_counter()
