@@ -112,6 +112,8 @@ uint32_t poasta_graph_aligned_nodes(const poasta_graph *g, uint32_t node, uint32
 /* Writers/readers. Output buffers are malloc'ed by the library; release with poasta_free_buffer. */
 int poasta_graph_to_fasta(const poasta_graph *g, char **out, size_t *len);      /* io/fasta.rs:69  */
 int poasta_graph_to_gfa(const poasta_graph *g, int v1, char **out, size_t *len);/* io/graph.rs:245,374 */
+/* dialect 0 = `view -O dot` (io/graph.rs:504), 1 = `align -O dot` (petgraph Dot, io/graph.rs:229) */
+int poasta_graph_to_dot(const poasta_graph *g, int dialect, char **out, size_t *len);
 int poasta_graph_save(const poasta_graph *g, char **out, size_t *len);          /* io/graph.rs:24  */
 int poasta_graph_load(const uint8_t *data, size_t len, poasta_graph **out);     /* io/graph.rs:30  */
 int poasta_graph_from_fasta_msa(const char *fasta, size_t len, poasta_graph **out); /* io/graph.rs:36 */

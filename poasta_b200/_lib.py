@@ -41,7 +41,7 @@ EXPORTS = [
     "poasta_graph_new", "poasta_graph_free", "poasta_graph_node_count",
     "poasta_graph_node_count_with_start_and_end", "poasta_graph_edge_count",
     "poasta_graph_num_sequences", "poasta_graph_add_alignment", "poasta_graph_get_view",
-    "poasta_graph_aligned_nodes", "poasta_graph_to_fasta", "poasta_graph_to_gfa",
+    "poasta_graph_aligned_nodes", "poasta_graph_to_fasta", "poasta_graph_to_gfa", "poasta_graph_to_dot",
     "poasta_graph_save", "poasta_graph_load", "poasta_graph_from_fasta_msa",
     "poasta_free_buffer", "poasta_msa_batch", "poasta_msa_batch_into", "poasta_version",
 ]
@@ -73,6 +73,7 @@ def load():
     for f in ("poasta_graph_to_fasta", "poasta_graph_save"):
         getattr(lib, f).argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.poasta_graph_to_gfa.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.poasta_graph_to_dot.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.poasta_graph_load.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
     lib.poasta_graph_from_fasta_msa.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
     lib.poasta_free_buffer.argtypes = [vp]

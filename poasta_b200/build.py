@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
     cli_src = os.path.join(CSRC, "cli_main.cpp")
     if os.path.exists(cli_src) and (force or _stale(CLI, deps + [OUT])):
         cmd = ["g++", "-O2", "-std=c++17", "-o", CLI, cli_src, "-L" + HERE, "-lposta_b200",
-               "-Wl,-rpath,$ORIGIN", "-pthread"]
+               "-Wl,-rpath,$ORIGIN", "-pthread", "-lz"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

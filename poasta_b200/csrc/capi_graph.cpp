@@ -77,6 +77,13 @@ int poasta_graph_to_gfa(const poasta_graph *h, int v1, char **out, size_t *len) 
     return emit(buf, out, len);
 }
 
+int poasta_graph_to_dot(const poasta_graph *h, int dialect, char **out, size_t *len) {
+    std::string buf;
+    if (dialect == 0) graph_to_dot_view(h->g, buf);
+    else graph_to_dot_petgraph(h->g, buf);
+    return emit(buf, out, len);
+}
+
 int poasta_graph_save(const poasta_graph *h, char **out, size_t *len) {
     std::string buf;
     graph_to_poasta(h->g, buf);

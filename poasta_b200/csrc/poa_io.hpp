@@ -5,6 +5,8 @@
 //   FASTA-MSA import      : /root/reference/src/io/graph.rs:36-103
 //   .poasta (bincode 1.3) : /root/reference/src/io/graph.rs:24-34 + poa.rs:84-94,484-489 (layout unpinned)
 #pragma once
+#include <charconv>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <sstream>
@@ -238,6 +240,103 @@ inline bool graph_to_gfa(const POAGraph &g, std::string &out, bool v1_paths) {
         }
     }
     return true;
+}
+
+// ---- DOT ----------------------------------------------------------------------------------------
+// `view -O dot`: io/graph.rs:504-609 (hand-written dialect). f64 Display = shortest round-trip digits.
+inline std::string fmt_f64(double v) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    return std::string(buf, r.ptr);
+}
+inline const char *graphviz_node_color(uint8_t c) {
+    switch (c) {
+        case 'A': return "#80BC42";
+        case 'C': return "#006DB6";
+        case 'G': return "#F36C3E";
+        case 'T': return "#B12028";
+        default: return "#939393";
+    }
+}
+inline void graph_to_dot_view(const POAGraph &g, std::string &out) {
+    out += "# seq:\t";
+    for (size_t i = 0; i < g.sequences.size(); ++i) {
+        if (i) out.push_back('\t');
+        out += g.sequences[i].name + ":" + std::to_string(g.sequences[i].start_node);
+    }
+    out += "\ndigraph {\nrankdir=\"LR\"\nnode [shape=square, style=filled, fillcolor=\"#e3e3e3\", penwidth=0]\n\n";
+    const uint32_t n = g.node_count_with_start_and_end();
+    for (uint32_t v = 0; v < n; ++v)
+        out += std::to_string(v) + " [label=\"" + std::string(1, (char)g.nodes[v].symbol) + "\"; fontcolor=\"" +
+               graphviz_node_color(g.nodes[v].symbol) + "\"]\n";
+    std::vector<uint8_t> done(n, 0);
+    for (uint32_t v = 0; v < n; ++v) {
+        if (done[v]) continue;
+        done[v] = 1;
+        if (!g.nodes[v].aligned_nodes.empty()) {
+            out += "{rank=same; " + std::to_string(v);
+            for (uint32_t a : g.nodes[v].aligned_nodes) out += "; " + std::to_string(a);
+            out += "}\n";
+        }
+        for (uint32_t a : g.nodes[v].aligned_nodes) done[a] = 1;
+    }
+    size_t max_num_seq = 0;
+    bool any_edge = false;
+    for (const auto &e : g.edges)
+        if (!e.vacant) {
+            max_num_seq = std::max(max_num_seq, e.sequence_ids.size());
+            any_edge = true;
+        }
+    if (!any_edge) max_num_seq = 1;
+    for (const auto &e : g.edges) {
+        if (e.vacant) continue;
+        const double frac = (double)e.sequence_ids.size() / (double)max_num_seq;
+        const long long weight = (long long)std::round(1.0 + frac * (40.0 - 1.0));
+        const double pen = 0.5 + frac * (3.5 - 0.5);
+        out += std::to_string(e.node[0]) + " -> " + std::to_string(e.node[1]) + " [weight=" + std::to_string(weight) +
+               "; penwidth=" + fmt_f64(pen) + "; label=" + std::to_string(e.sequence_ids.size()) + "; class=\"";
+        for (size_t i = 0; i < e.sequence_ids.size(); ++i) {
+            if (i) out.push_back(' ');
+            out += "s" + std::to_string(e.sequence_ids[i]);
+        }
+        out += "\"]\n";
+    }
+    out += "}\n";
+}
+
+// `align -O dot`: petgraph 0.6.5 `Dot` of the relabelled graph (io/graph.rs:229-243, poa.rs:473-499);
+// node label = format!("{:?} ({:?})", char, index), edge label = format!("{}, {:?}", weight, sequence_ids),
+// labels escaped the way petgraph's Display-escaper does (quote, backslash, newline). Layout restated from the
+// crate's published output format (unpinned).
+inline void graph_to_dot_petgraph(const POAGraph &g, std::string &out) {
+    auto esc = [](const std::string &s) {
+        std::string r;
+        for (char c : s) {
+            if (c == '"' || c == '\\') r.push_back('\\');
+            if (c == '\n') {
+                r += "\\l";
+                continue;
+            }
+            r.push_back(c);
+        }
+        return r;
+    };
+    out += "digraph {\n";
+    for (uint32_t v = 0; v < g.nodes.size(); ++v) {
+        std::string label = std::string("'") + (char)g.nodes[v].symbol + "' (" + std::to_string(v) + ")";
+        out += "    " + std::to_string(v) + " [ label = \"" + esc(label) + "\" ]\n";
+    }
+    for (const auto &e : g.edges) {
+        if (e.vacant) continue;
+        std::string label = std::to_string(e.weight) + ", [";
+        for (size_t i = 0; i < e.sequence_ids.size(); ++i) {
+            if (i) label += ", ";
+            label += std::to_string(e.sequence_ids[i]);
+        }
+        label += "]";
+        out += "    " + std::to_string(e.node[0]) + " -> " + std::to_string(e.node[1]) + " [ label = \"" + esc(label) + "\" ]\n";
+    }
+    out += "}\n\n";
 }
 
 // ---- FASTA-MSA import (io/graph.rs:36-103) ---------------------------------------------------

@@ -124,6 +124,9 @@ class POAGraph:
     def to_gfa(self, v1=False):
         return self._emit(self._lib.poasta_graph_to_gfa, 1 if v1 else 0)
 
+    def to_dot(self, petgraph_dialect=False):
+        return self._emit(self._lib.poasta_graph_to_dot, 1 if petgraph_dialect else 0)
+
     def save(self):
         return self._emit(self._lib.poasta_graph_save)
 
