@@ -196,7 +196,7 @@ int oracle_msa(const char *fasta, size_t fasta_len, const uint8_t *graph_in, siz
         uint32_t sc = 0;
         GraphError ge;
         if (g.is_empty()) {
-            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), nullptr, 0);
+            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), false, nullptr, 0);
         } else {
             flat.build(g);
             ncells += (uint64_t)g.node_count() * rec.seq.size();
@@ -206,7 +206,7 @@ int oracle_msa(const char *fasta, size_t fasta_len, const uint8_t *graph_in, siz
             st[0] += r.num_queued, st[1] += r.num_visited, st[2] += r.num_pruned;
             std::vector<AlignedPair> aln(r.rpos.size());
             for (size_t k = 0; k < aln.size(); ++k) aln[k] = {r.rpos[k], r.qpos[k]};
-            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), aln.data(), aln.size());
+            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), true, aln.data(), aln.size());
         }
         if (ge != GraphError::Ok) return -(int)ge - 2;
         if (scores && i < scores_cap) scores[i] = sc;

@@ -1037,7 +1037,7 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
             if (graphs[f]->g.is_empty()) {
                 const FastaRecord &rec = recs[f][round];
                 graphs[f]->flat_valid = false;
-                GraphError ge = graphs[f]->g.add_alignment_with_weights(rec.name, (const uint8_t *)rec.seq.data(), rec.seq.size(), nullptr, 0);
+                GraphError ge = graphs[f]->g.add_alignment_with_weights(rec.name, (const uint8_t *)rec.seq.data(), rec.seq.size(), false, nullptr, 0);
                 if (ge != GraphError::Ok) return POASTA_ERR_GRAPH_CYCLE;
                 if (scores_out) scores_out[score_base[f] + round] = 0;
             } else {
@@ -1076,7 +1076,7 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
                 return;
             }
             graphs[f]->flat_valid = false;
-            GraphError ge = graphs[f]->g.add_alignment_with_weights(rec.name, (const uint8_t *)rec.seq.data(), rec.seq.size(),
+            GraphError ge = graphs[f]->g.add_alignment_with_weights(rec.name, (const uint8_t *)rec.seq.data(), rec.seq.size(), true,
                                                                     pending[i].aln.data(), pending[i].aln.size());
             if (ge != GraphError::Ok) err = ge == GraphError::InvalidAlignment ? POASTA_ERR_INVALID_ALIGNMENT : POASTA_ERR_GRAPH_CYCLE;
             if (scores_out) scores_out[score_base[f] + round] = pending[i].score;

@@ -41,10 +41,10 @@ int poasta_graph_add_alignment(poasta_graph *h, const char *name, const uint8_t 
                                const uint32_t *qpos, uint32_t n_pairs, const uint64_t *weights) {
     if (!h || !name || (len && !seq)) return POASTA_ERR_INVALID_ARG;
     h->flat_valid = false;
-    if (!rpos || !qpos) return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, nullptr, 0, weights));
+    if (!rpos || !qpos) return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, false, nullptr, 0, weights));
     std::vector<AlignedPair> aln(n_pairs);
     for (uint32_t i = 0; i < n_pairs; ++i) aln[i] = {rpos[i], qpos[i]};
-    return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, aln.data(), n_pairs, weights));
+    return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, true, aln.data(), n_pairs, weights));
 }
 
 int poasta_graph_get_view(poasta_graph *h, poasta_graph_view *view) {

@@ -172,13 +172,14 @@ struct POAGraph {
         return true;
     }
 
-    // poa.rs:171-321. `aln == nullptr` is the reference's `alignment_opt == None`.
+    // poa.rs:171-321. `has_alignment == false` is the reference's `alignment_opt == None`; an EMPTY alignment is
+    // Some(&[]) and is rejected as InvalidAlignment for a non-empty sequence (poa.rs:210-224).
     // `weights == nullptr` means all ones (what the CLI passes, bin/poasta.rs:193).
-    GraphError add_alignment_with_weights(const std::string &name, const uint8_t *seq, size_t len,
+    GraphError add_alignment_with_weights(const std::string &name, const uint8_t *seq, size_t len, bool has_alignment,
                                           const AlignedPair *aln, size_t n_pairs,
                                           const uint64_t *weights = nullptr) {
         auto w = [&](size_t i) -> uint64_t { return weights ? weights[i] : 1; };
-        if (aln == nullptr) {
+        if (!has_alignment) {
             if (len == 0) {
                 sequences.push_back({name, start_node});
                 return post_process();

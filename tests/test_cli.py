@@ -85,8 +85,12 @@ def test_align_then_view_gfa(tmp_path):
 
 
 @pytest.mark.gpu
-def test_align_into_existing_graph_ends_free_path(tmp_path):
-    # config 5 shape: -I graph, -m ends-free, -H path (every read is also inserted, bin/poasta.rs:226)
+@pytest.mark.parametrize("span,mode,hname,heur", [("global", 0, "path", 2), ("ends-free", 1, "dijkstra", 0), ("ends-free", 1, "path", 2),
+                                                  ("semi-global", 1, "mingap", 1)])
+def test_align_into_existing_graph(tmp_path, span, mode, hname, heur):
+    # config 5 shape: -I graph, -m ends-free, -H path (every read is also inserted, bin/poasta.rs:226). The reference's
+    # ends-free search can return an empty alignment, which its graph insertion rejects (InvalidAlignment): whatever the
+    # oracle-driven run does — output bytes or error — the CLI must do the same.
     fa = open(os.path.join(ROOT, "tests", "golden", "test2_from_abpoa.fa"), "rb").read()
     recs = fa.split(b">")[1:]
     first, rest = b">" + b">".join(recs[:6]), b">" + b">".join(recs[6:])
@@ -94,8 +98,11 @@ def test_align_into_existing_graph_ends_free_path(tmp_path):
     (tmp_path / "rest.fa").write_bytes(rest)
     graph = tmp_path / "g.poasta"
     assert _run("align", "-o", str(graph), str(tmp_path / "first.fa")).returncode == 0
-    r = _run("align", "-I", str(graph), "-m", "ends-free", "-H", "path", "-O", "gfa", str(tmp_path / "rest.fa"))
-    assert r.returncode == 0
     rc, g0, _, _ = H.oracle_msa(first, fmt=3)
-    rc2, expect, _, _ = H.oracle_msa(rest, mode=1, heuristic=2, fmt=1, graph_in=g0)
-    assert rc == 0 and rc2 == 0 and r.stdout == expect
+    assert rc == 0 and graph.read_bytes() == g0
+    r = _run("align", "-I", str(graph), "-m", span, "-H", hname, "-O", "gfa", str(tmp_path / "rest.fa"))
+    rc2, expect, _, _ = H.oracle_msa(rest, mode=mode, heuristic=heur, fmt=1, graph_in=g0)
+    if rc2 == 0:
+        assert r.returncode == 0 and r.stdout == expect
+    else:
+        assert rc2 == -4 and r.returncode == 1 and b"poasta_status -4" in r.stderr
