@@ -303,13 +303,12 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
             view->symbol, si.dist_min.data(), si.dist_max.data(), si.is_exit.data(), si.bub_off.data(), si.bub.data(),
             si.path_off.empty() ? nullptr : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
     ScratchDims d(view->n_nodes, qlen, x, o, e);
-    std::vector<uint32_t> blk((size_t)d.nbr * d.nbc, 0), qhead((size_t)d.f_max * 3, 0), reached((size_t)view->n_nodes * d.rw, 0),
-        dfa((size_t)(view->n_nodes + 2) * 3, 0);
-    const uint32_t max_blocks = d.nbr * d.nbc, max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
-    std::vector<uint4> cells((size_t)max_blocks * 48);
+    std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), reached((size_t)view->n_nodes * d.rw, 0), dfa((size_t)(view->n_nodes + 2) * 3, 0);
+    const uint32_t max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
+    const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
+    std::vector<uint8_t> planes((size_t)3 * plane_elems * (cell16 ? 2 : 4), 0xFF);
     std::vector<Item> items(max_items);
-    Scratch s{blk.data(), (uint32_t *)cells.data(), qhead.data(), items.data(), reached.data(), dfa.data(),
-              d.nbc, d.rw, max_blocks, max_items, d.f_max};
+    Scratch s{planes.data(), qhead.data(), items.data(), reached.data(), dfa.data(), plane_elems, d.W, d.rw, max_items, d.f_max};
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
@@ -318,11 +317,11 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     if (cell16) {
         rp::Search<uint16_t> search(g, seq, qlen, p, s);
         r = search.run(out_r.data(), out_q.data(), ocap);
-        used_blocks = search.n_blocks, used_items = search.n_items;
+        used_items = search.n_items;
     } else {
         rp::Search<uint32_t> search(g, seq, qlen, p, s);
         r = search.run(out_r.data(), out_q.data(), ocap);
-        used_blocks = search.n_blocks, used_items = search.n_items;
+        used_items = search.n_items;
     }
     *score = r.score;
     *n_pairs = r.n_pairs;

@@ -42,7 +42,7 @@ struct BatchDev {
     const GraphDesc *graphs;
     const AlnDesc *alns;
     const uint8_t *node_sym;
-    const uint32_t *node_info, *node_id, *pred_off, *pred_rank;
+    const uint32_t *node_info, *node_id, *pred_off, *pred_rank, *pred_slot;
     const uint8_t *queries;
     uint32_t n_alns;
     int x, oe, e;
@@ -241,6 +241,10 @@ __global__ void __launch_bounds__(FILL_THREADS) dp_fill_kernel(BatchDev P) {
     }
 }
 
+}  // namespace poasta
+#include "dp_warp_kernel.cuh"
+namespace poasta {
+
 // gap_affine.rs:804-915 on the trace words. One thread per alignment.
 template <typename TraceT>
 __global__ void traceback_kernel(BatchDev P) {
@@ -413,7 +417,7 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sms = 0;
-    Buf graphs, alns, node_sym, node_info, node_id, pred_off, pred_rank, queries, scratch, trace, scores, counter, out_r, out_q,
+    Buf graphs, alns, node_sym, node_info, node_id, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
     Buf r_graphs, r_sym, r_is_exit, r_dist_min, r_dist_max, r_succ_off, r_succ, r_pred_off, r_pred, r_bub_off, r_bub, r_path_off,
@@ -476,7 +480,7 @@ struct ChunkResult {
 };
 
 // Runs one packed batch (must fit the memory budget) and leaves results in pinned host memory.
-static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_params &prm, ChunkResult &res) {
+static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_params &prm, ChunkResult &res, bool scores_only) {
     const uint32_t n = (uint32_t)pb.alns.size();
     if (n == 0) return 0;
     CK(cudaSetDevice(c.device));
@@ -486,16 +490,27 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     // slots: resident CTAs; bounded by scratch memory
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t per_slot = (size_t)pb.max_cells * 2 * sizeof(int);
-    size_t slots = (size_t)c.n_sms * 4;
-    slots = std::min<size_t>(slots, n);
+    // warp-per-alignment kernel when every query fits 32 lanes x 32 columns, else the CTA-per-alignment kernel
+    static const bool force_cta = getenv("POASTA_DP_KERNEL") && !strcmp(getenv("POASTA_DP_KERNEL"), "cta");
+    const bool use_warp = pb.max_W <= (uint32_t)WARP_MAX_W && !force_cta;
+    const size_t per_slot = use_warp ? (size_t)pb.max_store_cells * 2 * sizeof(int) : (size_t)pb.max_cells * 2 * sizeof(int);
+    size_t slots = (size_t)c.n_sms * 4;  // CTA slots of the CTA-per-alignment kernel
+    if (use_warp) {                      // warp slots: what the register file lets be resident
+        int ctas = 0;
+        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint16_t, false>, WARP_KERNEL_WARPS * 32, 0);
+        else if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint32_t, true>, WARP_KERNEL_WARPS * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint16_t, true>, WARP_KERNEL_WARPS * 32, 0);
+        slots = (size_t)c.n_sms * std::max(1, ctas) * WARP_KERNEL_WARPS;
+    }
+    slots = std::min<size_t>(slots, use_warp ? ((size_t)n + 3) / 4 * 4 : n);
     const size_t scratch_budget = std::max<size_t>(((size_t)8 << 30) / tl_lane_count, c.scratch.cap);
-    while (slots > 1 && slots * per_slot > scratch_budget) slots = std::max<size_t>(1, slots / 2);
-    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(pb.trace_elems * tsz)) return POASTA_ERR_CUDA;
+    while (slots > 4 && slots * per_slot > scratch_budget) slots = std::max<size_t>(4, slots / 2 / 4 * 4);
+    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(scores_only ? 16 : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
               c.node_id.reserve(pb.node_id.size() * 4) && c.pred_off.reserve(pb.pred_off.size() * 4) &&
-              c.pred_rank.reserve(pb.pred_rank.size() * 4 + 4) && c.queries.reserve(pb.queries.size() + 4) &&
+              c.pred_rank.reserve(pb.pred_rank.size() * 4 + 4) && c.pred_slot.reserve(pb.pred_slot.size() * 4 + 4) &&
+              c.queries.reserve(pb.queries.size() + 4) &&
               c.scores.reserve(n * 4) && c.counter.reserve(4) && c.out_r.reserve(pb.out_elems * 4) &&
               c.out_q.reserve(pb.out_elems * 4) && c.n_pairs.reserve(n * 4) && c.status.reserve(n * 4) &&
               c.offsets.reserve((n + 1) * 4);
@@ -507,8 +522,10 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaMemcpyAsync(c.node_info.d, pb.node_info.data(), pb.node_info.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.node_id.d, pb.node_id.data(), pb.node_id.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.pred_off.d, pb.pred_off.data(), pb.pred_off.size() * 4, cudaMemcpyHostToDevice, s));
-    if (!pb.pred_rank.empty())
+    if (!pb.pred_rank.empty()) {
         CK(cudaMemcpyAsync(c.pred_rank.d, pb.pred_rank.data(), pb.pred_rank.size() * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c.pred_slot.d, pb.pred_slot.data(), pb.pred_slot.size() * 4, cudaMemcpyHostToDevice, s));
+    }
     if (!pb.queries.empty()) CK(cudaMemcpyAsync(c.queries.d, pb.queries.data(), pb.queries.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(c.counter.d, 0, 4, s));
     CK(cudaMemsetAsync(c.scores.d, 0x3F, n * 4, s));
@@ -523,6 +540,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.node_id = (const uint32_t *)c.node_id.d;
     P.pred_off = (const uint32_t *)c.pred_off.d;
     P.pred_rank = (const uint32_t *)c.pred_rank.d;
+    P.pred_slot = (const uint32_t *)c.pred_slot.d;
     P.queries = (const uint8_t *)c.queries.d;
     P.n_alns = n;
     P.x = prm.mismatch;
@@ -539,8 +557,36 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.status = (int32_t *)c.status.d;
 
     CK(cudaEventRecord(c.ev0, s));
-    if (wide) dp_fill_kernel<uint32_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
-    else dp_fill_kernel<uint16_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
+    if (use_warp) {
+        const unsigned grid = (unsigned)(slots / WARP_KERNEL_WARPS), block = WARP_KERNEL_WARPS * 32;
+        if (scores_only) dp_fill_warp_kernel<uint16_t, false><<<grid, block, 0, s>>>(P);
+        else if (wide) dp_fill_warp_kernel<uint32_t, true><<<grid, block, 0, s>>>(P);
+        else dp_fill_warp_kernel<uint16_t, true><<<grid, block, 0, s>>>(P);
+    } else {
+        if (wide) dp_fill_kernel<uint32_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
+        else dp_fill_kernel<uint16_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
+    }
+    if (scores_only) {
+        CK(cudaEventRecord(c.ev1, s));
+        CK(cudaGetLastError());
+        if (!c.h_scores.reserve(n * 4)) return POASTA_ERR_CUDA;
+        CK(cudaMemcpyAsync(c.h_scores.h, c.scores.d, n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms0 = 0;
+        cudaEventElapsedTime(&ms0, c.ev0, c.ev1);
+        tl_kernel_ms += ms0;
+        tl_d2h += (uint64_t)n * 4;
+        tl_launches += 1;
+        tl_cells += pb.total_cells;
+        res.scores.assign((uint32_t *)c.h_scores.h, (uint32_t *)c.h_scores.h + n);
+        res.n_pairs.assign(n, 0);
+        res.offsets.assign(n + 1, 0);
+        res.status.assign(n, 0);
+        for (uint32_t i = 0; i < n; ++i)
+            if (res.scores[i] >= (uint32_t)INF) res.status[i] = POASTA_ERR_NO_ALIGNMENT;
+        res.dense_r = res.dense_q = nullptr;
+        return 0;
+    }
     const unsigned tb_blocks = (n + 127) / 128;
     if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
     else traceback_kernel<uint16_t><<<tb_blocks, 128, 0, s>>>(P);
@@ -599,7 +645,7 @@ struct Problem {
 
 // DP path: aligns all problems; calls sink(i, score, status, rpos*, qpos*, n_pairs) per problem in order.
 template <class Sink>
-static int dp_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
+static int dp_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink, bool scores_only = false) {
     DeviceContext &c = ctx_for(device);
     int rc = c.init(device);
     if (rc) return rc;
@@ -633,7 +679,7 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
             idx.push_back(i);
             ++i;
         }
-        rc = run_chunk(c, pb, prm, res);
+        rc = run_chunk(c, pb, prm, res, scores_only);
         if (rc) return rc;
         size_t k = 0;
         for (size_t t = 0; t < idx.size(); ++t) {
@@ -651,7 +697,8 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
                 }
                 continue;
             }
-            sink(idx[t], res.scores[k], res.status[k], res.dense_r + res.offsets[k], res.dense_q + res.offsets[k], res.n_pairs[k]);
+            sink(idx[t], res.scores[k], res.status[k], res.dense_r ? res.dense_r + res.offsets[k] : nullptr,
+                 res.dense_q ? res.dense_q + res.offsets[k] : nullptr, res.n_pairs[k]);
             ++k;
         }
     }
@@ -666,40 +713,25 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     CK(cudaSetDevice(c.device));
     const replay::ScratchDims dmax(pr.max_V, pr.max_Q, prm.mismatch, prm.gap_open, prm.gap_extend);
     auto up = [](uint64_t b) { return (b + 255) & ~(uint64_t)255; };
-    const uint64_t blk_entries = (uint64_t)dmax.nbr * dmax.nbc;
-    const uint64_t cells_per_aln = (uint64_t)pr.max_V * (pr.max_Q + 1);
+    const uint64_t cells_per_aln = (uint64_t)pr.max_V * dmax.W;
     // u16 score cells when no reachable score can hit 0xFFFF (all nodes deleted + all query bases inserted is the worst case)
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
     const bool cell16 = worst < 0xFF00u;
-    const uint64_t block_bytes = cell16 ? 384 : 768;
-    // the search touches a band of the table: size the per-worker arenas for that and retry the rare overflow at full size
-    uint64_t max_blocks = full_arenas ? blk_entries : std::min<uint64_t>(blk_entries, std::max<uint64_t>(4096, blk_entries * 9 / 20));
-    uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 131072 + cells_per_aln / 16;
-    uint64_t off_cells = up(blk_entries * 4);
+    const uint64_t plane_bytes = up(3 * cells_per_aln * (cell16 ? 2 : 4));
+    // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
+    uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 65536 + cells_per_aln / 24;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, std::min<uint64_t>((uint64_t)96 << 30, total_b / 2)) / tl_lane_count;
+    // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs
+    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(0.72 * (double)total_b)) / tl_lane_count;
     uint64_t slab = 0, off_qhead = 0, off_items = 0, off_reached = 0, off_dfa = 0;
-    auto layout = [&]() {
-        off_qhead = off_cells + up(max_blocks * block_bytes);
-        off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
-        off_reached = off_items + up(max_items * 16);
-        off_dfa = off_reached + up((uint64_t)pr.max_V * dmax.rw * 4);
-        slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 12);
-    };
-    layout();
-    // keep at least 2 workers per SM resident: shrink the cell arena (the search touches a band of the table) before
-    // shrinking the worker count; exhausted arenas are reported per alignment (RP_OUT_OF_BLOCKS) and retried at full size
+    off_qhead = plane_bytes;
+    off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
+    off_reached = off_items + up(max_items * 16);
+    off_dfa = off_reached + up((uint64_t)pr.max_V * dmax.rw * 4);
+    slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 12);
     const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
-    if (!full_arenas && slab * want_workers > budget && max_blocks > 4096) {
-        const uint64_t fixed = slab - up(max_blocks * block_bytes);
-        const uint64_t per = budget / want_workers;
-        uint64_t nb = per > fixed ? (per - fixed) / block_bytes : 0;
-        nb = std::max<uint64_t>(nb, std::min<uint64_t>(blk_entries, std::max<uint64_t>(4096, blk_entries / 4)));
-        max_blocks = std::min(max_blocks, nb);
-        layout();
-    }
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
     const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
     workers = ((workers + warps_per_cta - 1) / warps_per_cta) * warps_per_cta;
@@ -760,8 +792,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.prm = replay::Params{prm.mismatch, prm.gap_open, prm.gap_extend, prm.mode, prm.heuristic};
     B.slabs = (uint8_t *)c.r_slabs.d;
     B.slab_bytes = slab;
-    B.off_cells = off_cells, B.off_qhead = off_qhead, B.off_items = off_items, B.off_reached = off_reached, B.off_dfa = off_dfa;
-    B.max_blocks = (uint32_t)max_blocks, B.max_items = (uint32_t)max_items;
+    B.off_qhead = off_qhead, B.off_items = off_items, B.off_reached = off_reached, B.off_dfa = off_dfa;
+    B.max_items = (uint32_t)max_items;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;
     B.n_pairs = (uint32_t *)c.n_pairs.d;
@@ -776,7 +808,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
 
     CK(cudaEventRecord(c.ev0, s));
     {
-        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 24;
+        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 32;
         const dim3 grid((unsigned)(workers / warps_per_cta)), block(warps_per_cta * 32);
         if (cell16) {
             if (minb >= 32) replay_kernel<uint16_t, 32><<<grid, block, 0, s>>>(B);
@@ -911,7 +943,7 @@ static int align_problems(int device, const std::vector<Problem> &probs, const p
         rc = dp_problems(device, probs, dp_prm, [&](size_t i, uint32_t score, int32_t status, const uint32_t *, const uint32_t *, uint32_t) {
             dp_score[i] = score;
             dp_status[i] = status;
-        });
+        }, /*scores_only=*/true);
         if (rc) return rc;
     }
     return replay_problems(device, probs, prm,

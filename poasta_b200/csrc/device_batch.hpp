@@ -26,6 +26,7 @@ struct GraphDesc {
     uint32_t node_base;     // into node_sym / node_info / node_id
     uint32_t predoff_base;  // into pred_off (V + 1 entries)
     uint32_t max_in_degree;
+    uint32_t n_stored;      // rows that later rows read from the row store (warp kernel)
 };
 
 struct AlnDesc {
@@ -42,16 +43,20 @@ constexpr uint32_t INFO_ALWAYS_OPEN = 1u << 8;
 constexpr uint32_t INFO_HAS_SUCC = 1u << 9;
 constexpr uint32_t INFO_IS_END = 1u << 10;
 constexpr uint32_t INFO_IS_START = 1u << 11;
+constexpr uint32_t INFO_STORE = 1u << 12;  // some later row reads this row from the row store (warp kernel)
+constexpr uint32_t INFO_SLOT_SHIFT = 13;   // bits 13.. : index of the row inside the compact row store
 
 struct PackedBatch {
     std::vector<GraphDesc> graphs;
     std::vector<AlnDesc> alns;
     std::vector<uint8_t> node_sym;
-    std::vector<uint32_t> node_info, node_id, pred_off, pred_rank;
+    std::vector<uint32_t> node_info, node_id, pred_off, pred_rank, pred_slot;
     std::vector<uint8_t> queries;
     uint64_t trace_elems = 0;
     uint64_t out_elems = 0;
     uint64_t max_cells = 0;  // max over alignments of V * W
+    uint64_t max_store_cells = 0;  // max over alignments of n_stored * W (warp kernel's compact row store)
+    uint32_t max_W = 0;
     uint64_t total_cells = 0;  // sum of V_real * Q (the GCUPS numerator)
     uint32_t max_in_degree = 0;
 
@@ -63,9 +68,11 @@ struct PackedBatch {
         node_id.clear();
         pred_off.clear();
         pred_rank.clear();
+        pred_slot.clear();
         queries.clear();
-        trace_elems = out_elems = max_cells = total_cells = 0;
+        trace_elems = out_elems = max_cells = total_cells = max_store_cells = 0;
         max_in_degree = 0;
+        max_W = 0;
     }
 
     // Appends one graph; returns its id. `rank_scratch` avoids reallocation across calls.
@@ -107,6 +114,22 @@ struct PackedBatch {
             gd.max_in_degree = std::max(gd.max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
         }
         pred_off.push_back((uint32_t)pred_rank.size());
+        // rows read through the row store: every predecessor of a row that is not "single predecessor = previous row"
+        const uint32_t pr0 = pred_off[gd.predoff_base];
+        for (uint32_t r = 0; r < V; ++r) {
+            const uint32_t b = pred_off[gd.predoff_base + r], e2 = pred_off[gd.predoff_base + r + 1];
+            const bool fast = (e2 - b == 1) && pred_rank[b] == r - 1 && !(node_info[gd.node_base + r] & INFO_IS_END);
+            if (fast) continue;
+            for (uint32_t k = b; k < e2; ++k) node_info[gd.node_base + pred_rank[k]] |= INFO_STORE;
+        }
+        gd.n_stored = 0;
+        for (uint32_t r = 0; r < V; ++r)
+            if (node_info[gd.node_base + r] & INFO_STORE) node_info[gd.node_base + r] |= (gd.n_stored++) << INFO_SLOT_SHIFT;
+        pred_slot.resize(pred_rank.size());
+        for (uint32_t k = pr0; k < pred_rank.size(); ++k) {
+            const uint32_t pi = node_info[gd.node_base + pred_rank[k]];
+            pred_slot[k] = (pi & INFO_STORE) ? (pi >> INFO_SLOT_SHIFT) : 0xFFFFFFFFu;
+        }
         max_in_degree = std::max(max_in_degree, gd.max_in_degree);
         graphs.push_back(gd);
         return (uint32_t)graphs.size() - 1;
@@ -116,7 +139,7 @@ struct PackedBatch {
         AlnDesc a;
         a.graph = graph;
         a.Q = Q;
-        a.W = (Q + 1 + 3) & ~3u;
+        a.W = (Q + 1 + 7) & ~7u;
         a.query_base = (uint32_t)queries.size();
         queries.insert(queries.end(), q, q + Q);
         while (queries.size() & 3) queries.push_back(0);
@@ -127,6 +150,8 @@ struct PackedBatch {
         a.out_base = (uint32_t)out_elems;
         out_elems += a.out_cap;
         max_cells = std::max<uint64_t>(max_cells, V * a.W);
+        max_store_cells = std::max<uint64_t>(max_store_cells, (uint64_t)std::max<uint32_t>(1, graphs[graph].n_stored) * a.W);
+        max_W = std::max(max_W, a.W);
         total_cells += (V - 2) * Q;
         alns.push_back(a);
     }

@@ -50,7 +50,7 @@ struct Graph {  // node-id space, adjacency in the reference's order
     const uint8_t *sym;
     const uint32_t *dist_min, *dist_max;
     const uint8_t *is_exit;
-    const uint32_t *bub_off, *bub;      // triples
+    const uint32_t *bub_off, *bub;      // quadruples (exit, min_dist, max_dist, max(dist_min(exit), 1) - 1)
     const uint32_t *path_off, *path_rem;  // may be null unless heuristic == 2
 };
 
@@ -59,13 +59,14 @@ struct Item {
 };
 
 struct Scratch {  // one slab per in-flight alignment
-    uint32_t *blk;       // block pointer table, nbr * nbc entries (0 = not allocated, else block index + 1)
-    void *cells;         // max_blocks * 192 scores (u16 when every reachable score fits, else u32)
+    void *planes;        // visited table: three dense planes (M, D, I) of V * W scores (u16 when every reachable score fits,
+                         // else u32), all-ones = unvisited; what the reference keeps in a hash of 8x8 blocks (gap_affine.rs:442-548)
     uint32_t *qhead;     // f_max * 3 stack heads (0 = empty, else item index + 1)
     Item *items;         // max_items
     uint32_t *reached;   // V * rw bitmap words
     uint32_t *dfa;       // (V + 2) * 3
-    uint32_t nbc, rw, max_blocks, max_items, f_max;  // rw = row stride in words: bitmap words, then lo, then hi + 1 (0 = empty)
+    uint64_t plane_elems;  // V * W
+    uint32_t W, rw, max_items, f_max;  // W = plane row stride; rw = reached row stride: bitmap words, then lo, then hi + 1 (0 = empty)
 };
 
 struct Params {
@@ -81,6 +82,145 @@ struct Result {
     uint32_t num_queued, num_visited, num_pruned;
 };
 
+// ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) as ONE out-of-line function -------------------
+// Called from two places of the state machine (popped states and greedily matched children); keeping a single copy of
+// this code keeps the kernel's instruction footprint small (instruction-fetch stalls were 1/3 of all stalls, profiles/).
+// Arguments travel by value in registers. Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped.
+template <typename CellT>
+struct PruneCtx {
+    const CellT *m_plane;     // Match-state scores, V * W
+    const uint32_t *reached;  // V rows of rw words: bitmap, lo, hi + 1
+    const uint32_t *bub;      // quadruples (exit, min_dist_to_exit, max_dist_to_exit, max(dist_min(exit), 1) - 1)
+    uint32_t W, rw, Q, o, e;
+};
+
+RP_HD uint32_t rp_hi_bit(uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz(bits);
+#else
+    return 31 - __builtin_clz(bits);
+#endif
+}
+RP_HD uint32_t rp_lo_bit(uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+    return __ffs(bits) - 1;
+#else
+    return __builtin_ctz(bits);
+#endif
+}
+// largest member < lim, or UNV
+RP_HD uint32_t reached_prev(const uint32_t *row, uint32_t rw, uint32_t lim) {
+    const uint32_t lo = row[rw - 2], hi1 = row[rw - 1];
+    if (hi1 == 0 || lim <= lo) return UNV;
+    const uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
+    uint32_t w = i >> 5;
+    const uint32_t wlo = lo >> 5;
+    uint32_t bits = row[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
+    for (;;) {
+        if (bits) return w * 32 + rp_hi_bit(bits);
+        if (w == wlo) return UNV;
+        bits = row[--w];
+    }
+}
+// smallest member >= lim, or UNV
+RP_HD uint32_t reached_next(const uint32_t *row, uint32_t rw, uint32_t lim) {
+    const uint32_t lo = row[rw - 2], hi1 = row[rw - 1];
+    if (hi1 == 0 || lim >= hi1) return UNV;
+    const uint32_t i = lim < lo ? lo : lim;
+    uint32_t w = i >> 5;
+    const uint32_t whi = (hi1 - 1) >> 5;
+    uint32_t bits = row[w] & (0xFFFFFFFFu << (i & 31));
+    for (;;) {
+        if (bits) return w * 32 + rp_lo_bit(bits);
+        if (w == whi) return UNV;
+        bits = row[++w];
+    }
+}
+
+template <typename CellT>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+    constexpr CellT CUNV = (CellT)~(CellT)0;
+    bool wrapped = false;
+    auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
+    for (uint32_t k = bub_begin; k < bub_end; ++k) {
+        const uint32_t exit = c.bub[4 * k], min_d = c.bub[4 * k + 1], max_d = c.bub[4 * k + 2], mde = c.bub[4 * k + 3];
+        const uint32_t *row = c.reached + (size_t)exit * c.rw;
+        if (row[c.rw - 1] == 0) continue;  // no offset reached at this exit yet: can improve
+        if (node == exit) continue;
+        const uint32_t tmin = off + min_d, tmax = off + max_d;
+        if (tmax > c.Q) continue;
+        const CellT *mrow = c.m_plane + (size_t)exit * c.W;
+        auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
+            const CellT v = mrow[r];
+            if (v == CUNV) wrapped = true;
+            const uint32_t t = (uint32_t)v + plus;
+            if (t == UNV) wrapped = true;
+            return t;
+        };
+        // reached.rs:191-255
+        auto improve_at = [&](uint32_t x, uint32_t left, uint32_t right) -> bool {
+            uint32_t implicit;
+            if (left != UNV && right != UNV) {
+                const uint32_t il = S(left, gap(x - left));
+                const uint32_t gr = right - x;
+                const uint32_t ir = S(right, gap(gr));
+                implicit = gr > mde ? il : (il < ir ? il : ir);
+            } else if (right != UNV) {
+                const uint32_t gr = right - x;
+                const uint32_t ir = S(right, gap(gr));
+                if (gr > mde) return true;
+                implicit = ir;
+            } else if (left != UNV) {
+                implicit = S(left, gap(x - left));
+            } else {
+                return true;
+            }
+            return score < implicit;
+        };
+        bool can = false;
+        uint32_t prev = reached_prev(row, c.rw, tmin);
+        bool have_last = false;
+        uint32_t last = 0;
+        for (uint32_t nx = reached_next(row, c.rw, tmin); nx != UNV && nx <= tmax; nx = reached_next(row, c.rw, nx + 1)) {
+            const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
+            if (st == ST_D && S(nx, c.o) > score) {
+                can = true;
+                break;
+            }
+            if (prev != UNV && st == ST_I && S(prev, c.o) > score) {
+                can = true;
+                break;
+            }
+            if (improve_at(o1, prev, nx)) {
+                can = true;
+                break;
+            }
+            uint32_t o2 = nx - 1u;  // wraps for nx == 0 like the release build
+            if (o2 < tmin) o2 = tmin;
+            if (o2 > tmax) o2 = tmax;
+            if (o2 != o1 && improve_at(o2, prev, nx)) {
+                can = true;
+                break;
+            }
+            prev = nx;
+            last = o2;
+            have_last = true;
+        }
+        if (!can) {
+            const uint32_t next = reached_next(row, c.rw, tmax == UNV ? tmax : tmax + 1);
+            if (!have_last && improve_at(tmin, prev, next)) can = true;
+            else if ((!have_last || last < tmax) && improve_at(tmax, prev, next)) can = true;
+            else if (prev != UNV && st == ST_I && S(prev, c.o) > score) can = true;
+        }
+        if (wrapped) return 2;
+        if (!can) return 1;  // !all(can_improve)
+    }
+    return 0;
+}
+
 // CellT = uint16_t halves the table footprint (more alignments in flight); the host picks it only when the largest
 // possible score (every node deleted + every query base inserted) is below 0xFFFF.
 template <typename CellT>
@@ -91,7 +231,7 @@ struct Search {
     const uint32_t Q;
     const Params &p;
     Scratch &s;
-    uint32_t n_blocks = 0, n_items = 0, free_items = 0;  // free_items: LIFO list of popped item slots (index + 1)
+    uint32_t n_items = 0, free_items = 0;  // free_items: LIFO list of popped item slots (index + 1)
     uint32_t f_cur = 0, f_hi = 0;
     bool q_empty = true;
     int err = RP_OK;
@@ -101,42 +241,23 @@ struct Search {
     RP_HD bool sym_eq(uint32_t node, uint8_t c) const { return node == g.end || g.sym[node] == c; }
 
     // ---- visited table -------------------------------------------------------------------------
-    RP_NI CellT *cell(uint32_t node, uint32_t off, bool create) {
-        uint32_t *bp = s.blk + (size_t)(node >> 3) * s.nbc + (off >> 3);
-        uint32_t b = *bp;
-        if (b == 0) {
-            if (!create) return nullptr;
-            if (n_blocks >= s.max_blocks) {
-                err = RP_OUT_OF_BLOCKS;
-                return nullptr;
-            }
-            uint4 *c = reinterpret_cast<uint4 *>(static_cast<CellT *>(s.cells) + (size_t)n_blocks * 192);
-            for (int i = 0; i < (int)(12 * sizeof(CellT)); ++i) c[i] = uint4{UNV, UNV, UNV, UNV};
-            b = ++n_blocks;
-            *bp = b;
-        }
-        return static_cast<CellT *>(s.cells) + (size_t)(b - 1) * 192 + ((node & 7) * 8 + (off & 7)) * 3;
+    RP_HD CellT *cell(uint32_t node, uint32_t off, uint32_t st) const {
+        return static_cast<CellT *>(s.planes) + (size_t)st * s.plane_elems + (size_t)node * s.W + off;
     }
-    RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) {
-        const CellT *c = cell(node, off, false);
-        if (!c) return UNV;
-        const CellT v = c[st];
+    RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
+        const CellT v = *cell(node, off, st);
         return v == CUNV ? UNV : (uint32_t)v;
     }
-    RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
-        CellT *c = cell(node, off, true);
-        if (c) c[st] = (CellT)v;
-    }
+    RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) { *cell(node, off, st) = (CellT)v; }
     RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
-        CellT *c = cell(node, off, true);
-        if (!c) return false;
         if (sizeof(CellT) == 2 && v >= 0xFFFFu) {  // cannot happen when the host sized CellT correctly
             err = RP_SCORE_WRAP;
             return false;
         }
-        const CellT cur = c[st];
+        CellT *c = cell(node, off, st);
+        const CellT cur = *c;
         if (cur == CUNV || v < (uint32_t)cur) {
-            c[st] = (CellT)v;
+            *c = (CellT)v;
             return true;
         }
         return false;
@@ -250,113 +371,13 @@ struct Search {
             }
         }
     }
-    RP_HD static uint32_t hi_bit(uint32_t bits) {
-#if defined(__CUDA_ARCH__)
-        return 31 - __clz(bits);
-#else
-        return 31 - __builtin_clz(bits);
-#endif
-    }
-    RP_HD static uint32_t lo_bit(uint32_t bits) {
-#if defined(__CUDA_ARCH__)
-        return __ffs(bits) - 1;
-#else
-        return __builtin_ctz(bits);
-#endif
-    }
-    // largest member < lim, or UNV
-    RP_HD uint32_t reached_prev(const uint32_t *row, uint32_t lim) const {
-        const uint32_t lo = row[s.rw - 2], hi1 = row[s.rw - 1];
-        if (hi1 == 0 || lim <= lo) return UNV;
-        const uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
-        uint32_t w = i >> 5;
-        const uint32_t wlo = lo >> 5;
-        uint32_t bits = row[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
-        for (;;) {
-            if (bits) return w * 32 + hi_bit(bits);
-            if (w == wlo) return UNV;
-            bits = row[--w];
-        }
-    }
-    // smallest member >= lim, or UNV
-    RP_HD uint32_t reached_next(const uint32_t *row, uint32_t lim) const {
-        const uint32_t lo = row[s.rw - 2], hi1 = row[s.rw - 1];
-        if (hi1 == 0 || lim >= hi1) return UNV;
-        const uint32_t i = lim < lo ? lo : lim;
-        uint32_t w = i >> 5;
-        const uint32_t whi = (hi1 - 1) >> 5;
-        uint32_t bits = row[w] & (0xFFFFFFFFu << (i & 31));
-        for (;;) {
-            if (bits) return w * 32 + lo_bit(bits);
-            if (w == whi) return UNV;
-            bits = row[++w];
-        }
-    }
-
-    // reached.rs:191-255
-    RP_NI bool can_improve_at(uint32_t exit, uint32_t off, uint32_t score, uint32_t left, uint32_t right, uint32_t min_dist_to_end) {
-        uint32_t implicit;
-        if (left != UNV && right != UNV) {
-            const uint32_t il = add(get(exit, left, ST_M), gap_cost(ST_M, off - left));
-            const uint32_t gr = right - off;
-            const uint32_t ir = add(get(exit, right, ST_M), gap_cost(ST_M, gr));
-            implicit = gr > min_dist_to_end ? il : (il < ir ? il : ir);
-        } else if (right != UNV) {
-            const uint32_t gr = right - off;
-            const uint32_t ir = add(get(exit, right, ST_M), gap_cost(ST_M, gr));
-            if (gr > min_dist_to_end) return true;
-            implicit = ir;
-        } else if (left != UNV) {
-            implicit = add(get(exit, left, ST_M), gap_cost(ST_M, off - left));
-        } else {
-            return true;
-        }
-        return score < implicit;
-    }
-
-    // reached.rs:38-189
-    RP_NI bool can_improve_bubble(uint32_t exit, uint32_t min_d, uint32_t max_d, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
-        const uint32_t *row = s.reached + (size_t)exit * s.rw;
-        // is_empty(): any reached offset at this exit
-        if (row[s.rw - 1] == 0) return true;
-        if (node == exit) return true;
-        const uint32_t tmin = off + min_d, tmax = off + max_d;
-        const uint32_t a = g.dist_min[exit];
-        const uint32_t mde = a ? a - 1 : 0;
-        if (tmax > Q) return true;
-        uint32_t prev = reached_prev(row, tmin);
-        bool have_last = false;
-        uint32_t last = 0;
-        for (uint32_t nx = reached_next(row, tmin); nx != UNV && nx <= tmax; nx = reached_next(row, nx + 1)) {
-            const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
-            if (st == ST_D) {
-                if (add(get(exit, nx, ST_M), p.o) > score) return true;
-            }
-            if (prev != UNV && st == ST_I) {
-                if (add(get(exit, prev, ST_M), p.o) > score) return true;
-            }
-            if (can_improve_at(exit, o1, score, prev, nx, mde)) return true;
-            uint32_t o2 = nx - 1u;  // wraps for nx == 0 like the release build
-            if (o2 < tmin) o2 = tmin;
-            if (o2 > tmax) o2 = tmax;
-            if (o2 != o1 && can_improve_at(exit, o2, score, prev, nx, mde)) return true;
-            prev = nx;
-            last = o2;
-            have_last = true;
-        }
-        const uint32_t next = reached_next(row, tmax == UNV ? tmax : tmax + 1);
-        if (!have_last && can_improve_at(exit, tmin, score, prev, next, mde)) return true;
-        if ((!have_last || last < tmax) && can_improve_at(exit, tmax, score, prev, next, mde)) return true;
-        if (prev != UNV && st == ST_I) {
-            if (add(get(exit, prev, ST_M), p.o) > score) return true;
-        }
-        return false;
-    }
-
     RP_HD bool prune(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
-        for (uint32_t k = g.bub_off[node]; k < g.bub_off[node + 1]; ++k)
-            if (!can_improve_bubble(g.bub[3 * k], g.bub[3 * k + 1], g.bub[3 * k + 2], node, off, st, score)) return true;
-        return false;
+        const uint32_t b = g.bub_off[node], e = g.bub_off[node + 1];
+        if (b == e) return false;
+        PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.reached, g.bub, s.W, s.rw, Q, p.o, p.e};
+        const int r = prune_eval<CellT>(c, b, e, node, off, st, score);
+        if (r == 2) err = RP_SCORE_WRAP;
+        return r == 1;
     }
 
     RP_HD bool is_end(uint32_t node, uint32_t off, uint32_t st) const {  // gap_affine.rs:185-248, Unbounded bounds
@@ -617,10 +638,9 @@ struct Search {
 
 // scratch sizing shared by host and device code
 struct ScratchDims {
-    uint32_t nbr, nbc, rw, f_max;
+    uint32_t W, rw, f_max;
     RP_HD ScratchDims(uint32_t V, uint32_t Q, uint32_t x, uint32_t o, uint32_t e) {
-        nbr = (V >> 3) + 1;
-        nbc = ((Q + 1) >> 3) + 1;
+        W = (Q + 2 + 7) & ~7u;  // offsets 0..Q (+1: the reference relaxes I(v, Q+1) in one corner case, gap_affine.rs:360)
         rw = (Q + 1 + 31) / 32 + 2;  // + 2: [lo, hi + 1] of the row's members
         uint32_t m = x > o + e ? x : o + e;
         if (m == 0) m = 1;

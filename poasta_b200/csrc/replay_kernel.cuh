@@ -25,8 +25,8 @@ struct ReplayDev {
     uint32_t n_alns;
     replay::Params prm;
     uint8_t *slabs;
-    uint64_t slab_bytes, off_cells, off_qhead, off_items, off_reached, off_dfa;  // byte offsets inside a slab (blk at 0)
-    uint32_t max_blocks, max_items;
+    uint64_t slab_bytes, off_qhead, off_items, off_reached, off_dfa;  // byte offsets inside a slab (score planes at 0)
+    uint32_t max_items;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
     uint32_t *stats;  // per alignment: queued, visited, pruned, blocks
@@ -49,12 +49,13 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
         const AlnDesc ad = B.alns[a];
         const RGraphDesc gd = B.graphs[ad.graph];
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
-        // zero the block-pointer table, the bucket heads and the reached bitmaps (sizes of THIS alignment)
+        // reset the slab for THIS alignment with 128-bit stores: score planes to all-ones (unvisited), bucket heads and
+        // reached bitmaps to zero
         {
-            const uint4 z = make_uint4(0, 0, 0, 0);
+            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), z = make_uint4(0, 0, 0, 0);
             uint4 *p0 = reinterpret_cast<uint4 *>(slab);
-            const uint32_t n0 = ((uint64_t)dims.nbr * dims.nbc + 3) / 4;
-            for (uint32_t i = lane; i < n0; i += 32) p0[i] = z;
+            const uint64_t n0 = ((uint64_t)3 * gd.V * dims.W * sizeof(CellT) + 15) / 16;
+            for (uint64_t i = lane; i < n0; i += 32) p0[i] = ones;
             uint4 *p1 = reinterpret_cast<uint4 *>(slab + B.off_qhead);
             const uint32_t n1 = ((uint64_t)dims.f_max * 3 + 3) / 4;
             for (uint32_t i = lane; i < n1; i += 32) p1[i] = z;
@@ -75,25 +76,25 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             g.dist_max = B.dist_max + gd.node_base;
             g.is_exit = B.is_exit + gd.node_base;
             g.bub_off = B.bub_off + gd.buboff_base;
-            g.bub = B.bub + (uint64_t)gd.bub_base * 3;
+            g.bub = B.bub + (uint64_t)gd.bub_base * 4;
             g.path_off = B.path_off + gd.pathoff_base;
             g.path_rem = B.path_rem + gd.path_base;
             replay::Scratch s;
-            s.blk = reinterpret_cast<uint32_t *>(slab);
-            s.cells = slab + B.off_cells;
+            s.planes = slab;
+            s.plane_elems = (uint64_t)gd.V * dims.W;
             s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
             s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
             s.reached = reinterpret_cast<uint32_t *>(slab + B.off_reached);
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
-            s.nbc = dims.nbc, s.rw = dims.rw, s.f_max = dims.f_max;
-            s.max_blocks = B.max_blocks, s.max_items = B.max_items;
+            s.W = dims.W, s.rw = dims.rw, s.f_max = dims.f_max;
+            s.max_items = B.max_items;
             replay::Search<CellT> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;
             B.status[a] = r.status;
             B.stats[4 * a + 0] = r.num_queued, B.stats[4 * a + 1] = r.num_visited, B.stats[4 * a + 2] = r.num_pruned;
-            B.stats[4 * a + 3] = search.n_blocks;
+            B.stats[4 * a + 3] = search.n_items;
         }
         __syncwarp();
     }
@@ -127,7 +128,7 @@ struct PackedReplay {
         gd.pathoff_base = (uint32_t)path_off.size();
         gd.succ_base = (uint32_t)succ.size();
         gd.pred_base = (uint32_t)pred.size();
-        gd.bub_base = (uint32_t)(bub.size() / 3);
+        gd.bub_base = (uint32_t)(bub.size() / 4);
         gd.path_base = (uint32_t)path_rem.size();
         sym.insert(sym.end(), v.symbol, v.symbol + V);
         is_exit.insert(is_exit.end(), si.is_exit.begin(), si.is_exit.end());

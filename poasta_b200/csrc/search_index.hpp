@@ -19,7 +19,7 @@ struct SearchIndex {
     std::vector<uint32_t> dist_min, dist_max;  // shortest / longest path length to `end`
     std::vector<uint8_t> is_exit;
     std::vector<uint32_t> bub_off;  // V + 1
-    std::vector<uint32_t> bub;      // triples (exit, min_dist_to_exit, max_dist_to_exit)
+    std::vector<uint32_t> bub;      // quadruples (exit, min_dist_to_exit, max_dist_to_exit, max(dist_min(exit), 1) - 1)
     std::vector<uint32_t> path_off;  // V + 1 (only when the path heuristic is requested)
     std::vector<uint32_t> path_rem;  // remaining path length for the first <= 5 sampled paths through a node
 
@@ -169,8 +169,9 @@ struct SearchIndex {
                 bub.push_back(b.exit);
                 bub.push_back(b.min_d);
                 bub.push_back(b.max_d);
+                bub.push_back(dist_min[b.exit] ? dist_min[b.exit] - 1 : 0);  // min_dist_to_end used by the prune test (reached.rs:57-58)
             }
-            bub_off[n + 1] = (uint32_t)(bub.size() / 3);
+            bub_off[n + 1] = (uint32_t)(bub.size() / 4);
         }
         path_off.clear();
         path_rem.clear();
