@@ -505,7 +505,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     slots = std::min<size_t>(slots, use_warp ? ((size_t)n + 3) / 4 * 4 : n);
     const size_t scratch_budget = std::max<size_t>(((size_t)8 << 30) / tl_lane_count, c.scratch.cap);
     while (slots > 4 && slots * per_slot > scratch_budget) slots = std::max<size_t>(4, slots / 2 / 4 * 4);
-    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(scores_only ? 16 : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;
+    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve((scores_only && use_warp) ? 16 : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
               c.node_id.reserve(pb.node_id.size() * 4) && c.pred_off.reserve(pb.pred_off.size() * 4) &&
@@ -720,11 +720,13 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     const bool cell16 = worst < 0xFF00u;
     const uint64_t plane_bytes = up(3 * cells_per_aln * (cell16 ? 2 : 4));
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
-    uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 65536 + cells_per_aln / 24;
+    // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
+    uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 32768 + cells_per_aln / 32;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs
-    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(0.72 * (double)total_b)) / tl_lane_count;
+    static const double slab_fraction = getenv("POASTA_SLAB_FRACTION") ? atof(getenv("POASTA_SLAB_FRACTION")) : 0.6;
+    const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(slab_fraction * (double)total_b)) / tl_lane_count;
     uint64_t slab = 0, off_qhead = 0, off_items = 0, off_reached = 0, off_dfa = 0;
     off_qhead = plane_bytes;
     off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
@@ -936,7 +938,7 @@ static int align_problems(int device, const std::vector<Problem> &probs, const p
     std::vector<int32_t> dp_status(probs.size(), 0);
     poasta_params dp_prm = prm;
     dp_prm.tiebreak = 1;
-    bool any_q0 = false;
+    bool any_q0 = getenv("POASTA_SKIP_DP_CHECK") != nullptr;  // debugging aid: run the search alone
     for (const Problem &p : probs) any_q0 |= (p.qlen == 0);
     int rc = 0;
     if (!any_q0) {

@@ -188,3 +188,14 @@ def test_full_size_config2_family():
     assert len(msa) == 20 and len({len(r) for _, r in msa}) <= 2  # rows differ by at most the leading-gap quirk
     for name, row in msa:
         assert row.replace(b"-", b"") == seqs[name]
+
+
+def test_query_longer_than_warp_kernel_limit():
+    """Queries of 1024+ bases take the CTA-per-alignment DP kernel (the warp kernel covers 32 x 32 columns): both tiebreak
+    modes must stay exact there (regression: the score pass once ran that kernel without a trace store)."""
+    fa = synth.config2_family(41, n_seqs=4, root_len=1100, rate=0.04)
+    graphs, scores, _ = msa_batch([fa])
+    rc, expect, osc, _ = H.oracle_msa(fa)
+    assert rc == 0 and list(scores[0]) == list(osc) and graphs[0].to_fasta() == expect
+    for g, seq, sc, pairs in _progressive_cases(fa, max_align=2):
+        _check_both_modes(g, seq, sc, pairs)
