@@ -36,6 +36,12 @@ ALG_BYTES_PER_CU = 1.0      # traceback budget 1 B/CU; scores st
 ALG_INT_OPS_PER_CU = 12.0   # 6*d_v + 6 at in-degree 1
 
 
+def measured_traffic():
+    """DRAM bytes per cell update of each kernel from the committed ncu captures (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -221,9 +227,12 @@ def main():
         gcups_e2e = cells / wall_max / 1e9
         per_rank_cells = cells / world
         # roofline of the dominant kernel of the step (by device time)
-        dominant = "replay_kernel (order-exact search)" if search_ms > dp_ms else "dp_fill_kernel"
+        dominant = "replay_kernel (order-exact search)" if search_ms > dp_ms else "dp_fill kernels"
         dom_ms = max(search_ms, dp_ms)
         achieved = per_rank_cells * ALG_BYTES_PER_CU / (dom_ms / 1e3) / 1e9
+        tr = measured_traffic().get("replay_kernel" if search_ms > dp_ms else "dp_fill_warp_kernel")
+        n_dom_launches = max(1, int(launches / world) // (3 if tiebreak == TIEBREAK_EXACT else 4))
+        traffic = tr["dram_bytes_per_cu"] * per_rank_cells / n_dom_launches if tr else None
         dp_gbs = per_rank_cells * ALG_BYTES_PER_CU / (dp_ms / 1e3) / 1e9 if dp_ms else None
         line = {
             "metric": "GCUPS", "value": gcups_dev, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -236,13 +245,27 @@ def main():
                     "d2h_bytes_per_step": d2h / world / args.steps, "seqs_per_s": nseq / wall_max},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                         "traffic_note": (f"ncu dram__bytes_read+write = {tr['dram_bytes_per_cu']:.2f} B per cell update ({tr['capture']}), "
+                                          "scaled to the average launch of this run") if tr else "no ncu capture",
                          "note": "algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) x cells of the step / "
                                  "kernel time (CUDA events). dp_fill_kernel alone: "
                                  + (f"{dp_gbs:.1f} GB/s = {dp_gbs / peak:.4f} of peak, "
                                     f"{per_rank_cells * ALG_INT_OPS_PER_CU / (dp_ms / 1e3) / 1e12:.3f} Tint-op/s at 12 ops/CU" if dp_ms else "n/a")},
             "clocks": clocks,
         }
+        if world == 1 and tiebreak == TIEBREAK_EXACT and not args.no_cpu_baseline:
+            # the same workload through the DP-only mode (optimal scores, co-optimal alignments; not bit-exact at ties)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g2, s2, c2 = msa_batch(batches[0], device=local, tiebreak=TIEBREAK_DP)
+            w2 = time.perf_counter() - t0
+            k2, _, _ = aligner.last_batch_stats()
+            del g2
+            line["dp_only_mode"] = {"e2e_gcups": c2 / w2 / 1e9, "seqs_per_s": sum(len(x) for x in s2) / w2, "ms_per_step": w2 * 1e3,
+                                    "kernel_gcups": c2 / (k2 / 1e3) / 1e9,
+                                    "note": "tiebreak=dp on step 0's batch after the timed region; kernel time is the sum over "
+                                            "concurrent pipeline lanes"}
         if world == 1 and not args.no_cpu_baseline:
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
             cores = os.cpu_count() or 1

@@ -36,6 +36,15 @@ struct alignas(16) uint4 {
 };
 #endif
 
+// optional cycle accounting of the device build (-DRP_PROFILE): where a worker's time goes
+#if defined(RP_PROFILE) && defined(__CUDA_ARCH__)
+#define RP_T0 const long long _t0 = clock64()
+#define RP_ACC(x) x += clock64() - _t0
+#else
+#define RP_T0
+#define RP_ACC(x)
+#endif
+
 namespace poasta {
 namespace replay {
 
@@ -231,7 +240,11 @@ struct Search {
     const uint32_t Q;
     const Params &p;
     Scratch &s;
-    uint32_t n_items = 0, free_items = 0;  // free_items: LIFO list of popped item slots (index + 1)
+    uint32_t n_items = 0, free_items = 0;
+#if defined(RP_PROFILE)
+    long long prof_prune = 0, prof_push = 0, prof_pop = 0;
+    uint32_t prof_n_prune = 0;
+#endif  // free_items: LIFO list of popped item slots (index + 1)
     uint32_t f_cur = 0, f_hi = 0;
     bool q_empty = true;
     int err = RP_OK;
@@ -306,6 +319,7 @@ struct Search {
 
     // ---- bucket queue ---------------------------------------------------------------------------------
     RP_HD void push(uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+        RP_T0;
         const uint32_t f = score + h(node, off, st);
         if (f >= s.f_max) {
             err = RP_PRIORITY_RANGE;
@@ -332,6 +346,7 @@ struct Search {
             if (f < f_cur) f_cur = f;
             if (f > f_hi) f_hi = f;
         }
+        RP_ACC(prof_push);
     }
     RP_HD bool pop(Item &out, uint32_t &st) {
         if (q_empty) return false;
@@ -372,11 +387,16 @@ struct Search {
         }
     }
     RP_HD bool prune(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
+        RP_T0;
         const uint32_t b = g.bub_off[node], e = g.bub_off[node + 1];
         if (b == e) return false;
         PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.reached, g.bub, s.W, s.rw, Q, p.o, p.e};
         const int r = prune_eval<CellT>(c, b, e, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
+        RP_ACC(prof_prune);
+#if defined(RP_PROFILE)
+        ++prof_n_prune;
+#endif
         return r == 1;
     }
 

@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
             s.W = dims.W, s.rw = dims.rw, s.f_max = dims.f_max;
             s.max_items = B.max_items;
+#if defined(RP_PROFILE)
+            const long long t_begin = clock64();
+#endif
             replay::Search<CellT> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             B.scores[a] = r.score;
@@ -95,6 +98,17 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             B.status[a] = r.status;
             B.stats[4 * a + 0] = r.num_queued, B.stats[4 * a + 1] = r.num_visited, B.stats[4 * a + 2] = r.num_pruned;
             B.stats[4 * a + 3] = search.n_items;
+#if defined(RP_PROFILE)
+            {
+                static_assert(true, "");
+                const long long total = clock64() - t_begin;
+                if (a < 8)
+                    printf("aln %u: total %lld cyc, prune %lld (%.1f%%, %u calls, %lld cyc/call), push %lld (%.1f%%), visited %u queued %u pruned %u -> %lld cyc/visit\n",
+                           a, total, search.prof_prune, 100.0 * search.prof_prune / total, search.prof_n_prune,
+                           search.prof_prune / (search.prof_n_prune ? search.prof_n_prune : 1), search.prof_push,
+                           100.0 * search.prof_push / total, r.num_visited, r.num_queued, r.num_pruned, total / (r.num_visited ? r.num_visited : 1));
+            }
+#endif
         }
         __syncwarp();
     }
