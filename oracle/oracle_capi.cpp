@@ -299,16 +299,24 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     using rp::ScratchDims;
     poasta::SearchIndex si;
     si.build(*view, heuristic == 2);
-    rp::Graph g{view->n_nodes, view->start_node, view->end_node, view->succ_off, view->succ, view->pred_off, view->pred,
-            view->symbol, si.dist_min.data(), si.dist_max.data(), si.is_exit.data(), si.bub_off.data(), si.bub.data(),
-            si.path_off.empty() ? nullptr : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
+    std::vector<rp::NodeRec> recs;
+    si.node_records(*view, recs);
+    std::vector<uint32_t> path_off_zero;
+    if (si.path_off.empty()) path_off_zero.assign(view->n_nodes + 1, 0);
+    rp::Graph g{view->n_nodes, view->start_node, view->end_node, recs.data(), view->succ, view->pred, si.bub.data(),
+                si.path_off.empty() ? path_off_zero.data() : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
     ScratchDims d(view->n_nodes, qlen, x, o, e);
-    std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), reached((size_t)view->n_nodes * d.rw, 0), dfa((size_t)(view->n_nodes + 2) * 3, 0);
+    std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), qwin(rp::QWIN * 3, 0), rb((size_t)view->n_nodes * 2, 0),
+        dfa((size_t)(view->n_nodes + 2) * 6, 0);
     const uint32_t max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
     const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
-    std::vector<uint8_t> planes((size_t)3 * plane_elems * (cell16 ? 2 : 4), 0xFF);
+    std::vector<uint8_t> planes((size_t)3 * plane_elems * (cell16 ? 2 : 4));
+    if (cell16) std::fill((uint16_t *)planes.data(), (uint16_t *)planes.data() + 3 * plane_elems, (uint16_t)0x7FFF);
+    else std::fill((uint32_t *)planes.data(), (uint32_t *)planes.data() + 3 * plane_elems, 0x7FFFFFFFu);
     std::vector<Item> items(max_items);
-    Scratch s{planes.data(), qhead.data(), items.data(), reached.data(), dfa.data(), plane_elems, d.W, d.rw, max_items, d.f_max};
+    std::vector<uint32_t> free_slots(max_items);
+    Scratch s{planes.data(), qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), plane_elems, d.W,
+              max_items, d.f_max};
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);

@@ -420,8 +420,7 @@ struct DeviceContext {
     Buf graphs, alns, node_sym, node_info, node_id, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
-    Buf r_graphs, r_sym, r_is_exit, r_dist_min, r_dist_max, r_succ_off, r_succ, r_pred_off, r_pred, r_bub_off, r_bub, r_path_off,
-        r_path_rem, r_slabs, r_stats;
+    Buf r_graphs, r_nodes, r_succ, r_pred, r_bub, r_path_off, r_path_rem, r_slabs, r_stats;
     PinBuf h_stats;
     double last_kernel_ms = 0;
     uint32_t last_launches = 0;
@@ -717,7 +716,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     // u16 score cells when no reachable score can hit 0xFFFF (all nodes deleted + all query bases inserted is the worst case)
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
-    const bool cell16 = worst < 0xFF00u;
+    const bool cell16 = worst < 0x7F00u;  // the top bit of a cell is the reached mark
     const uint64_t plane_bytes = up(3 * cells_per_aln * (cell16 ? 2 : 4));
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
@@ -727,12 +726,13 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs
     static const double slab_fraction = getenv("POASTA_SLAB_FRACTION") ? atof(getenv("POASTA_SLAB_FRACTION")) : 0.6;
     const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(slab_fraction * (double)total_b)) / tl_lane_count;
-    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_reached = 0, off_dfa = 0;
+    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_dfa = 0;
     off_qhead = plane_bytes;
     off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
-    off_reached = off_items + up(max_items * 16);
-    off_dfa = off_reached + up((uint64_t)pr.max_V * dmax.rw * 4);
-    slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 12);
+    off_free = off_items + up(max_items * 16);
+    off_reached = off_free + up(max_items * 4);                   // reached bounds: 2 words per node
+    off_dfa = off_reached + up((uint64_t)pr.max_V * 8);
+    slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);           // DFA frames: 6 words
     const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
     const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
@@ -742,11 +742,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         if (!c.r_slabs.reserve(workers * slab)) return POASTA_ERR_CUDA;
     }
     bool ok = c.r_graphs.reserve(pr.graphs.size() * sizeof(RGraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
-              c.r_sym.reserve(pr.sym.size() + 4) && c.r_is_exit.reserve(pr.is_exit.size() + 4) &&
-              c.queries.reserve(pr.queries.size() + 4) && c.r_dist_min.reserve(pr.dist_min.size() * 4 + 4) &&
-              c.r_dist_max.reserve(pr.dist_max.size() * 4 + 4) && c.r_succ_off.reserve(pr.succ_off.size() * 4 + 4) &&
-              c.r_succ.reserve(pr.succ.size() * 4 + 4) && c.r_pred_off.reserve(pr.pred_off.size() * 4 + 4) &&
-              c.r_pred.reserve(pr.pred.size() * 4 + 4) && c.r_bub_off.reserve(pr.bub_off.size() * 4 + 4) &&
+              c.r_nodes.reserve(pr.nodes.size() * sizeof(replay::NodeRec) + 32) && c.queries.reserve(pr.queries.size() + 4) &&
+              c.r_succ.reserve(pr.succ.size() * 4 + 4) && c.r_pred.reserve(pr.pred.size() * 4 + 4) &&
               c.r_bub.reserve(pr.bub.size() * 4 + 4) && c.r_path_off.reserve(pr.path_off.size() * 4 + 4) &&
               c.r_path_rem.reserve(pr.path_rem.size() * 4 + 4) && c.scores.reserve(n * 4) && c.counter.reserve(4) &&
               c.out_r.reserve(pr.out_elems * 4) && c.out_q.reserve(pr.out_elems * 4) && c.n_pairs.reserve(n * 4) &&
@@ -759,16 +756,10 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     };
     CK(h2d(c.r_graphs, pr.graphs.data(), pr.graphs.size() * sizeof(RGraphDesc)));
     CK(h2d(c.alns, pr.alns.data(), n * sizeof(AlnDesc)));
-    CK(h2d(c.r_sym, pr.sym.data(), pr.sym.size()));
-    CK(h2d(c.r_is_exit, pr.is_exit.data(), pr.is_exit.size()));
+    CK(h2d(c.r_nodes, pr.nodes.data(), pr.nodes.size() * sizeof(replay::NodeRec)));
     CK(h2d(c.queries, pr.queries.data(), pr.queries.size()));
-    CK(h2d(c.r_dist_min, pr.dist_min.data(), pr.dist_min.size() * 4));
-    CK(h2d(c.r_dist_max, pr.dist_max.data(), pr.dist_max.size() * 4));
-    CK(h2d(c.r_succ_off, pr.succ_off.data(), pr.succ_off.size() * 4));
     CK(h2d(c.r_succ, pr.succ.data(), pr.succ.size() * 4));
-    CK(h2d(c.r_pred_off, pr.pred_off.data(), pr.pred_off.size() * 4));
     CK(h2d(c.r_pred, pr.pred.data(), pr.pred.size() * 4));
-    CK(h2d(c.r_bub_off, pr.bub_off.data(), pr.bub_off.size() * 4));
     CK(h2d(c.r_bub, pr.bub.data(), pr.bub.size() * 4));
     CK(h2d(c.r_path_off, pr.path_off.data(), pr.path_off.size() * 4));
     CK(h2d(c.r_path_rem, pr.path_rem.data(), pr.path_rem.size() * 4));
@@ -777,16 +768,10 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     ReplayDev B;
     B.graphs = (const RGraphDesc *)c.r_graphs.d;
     B.alns = (const AlnDesc *)c.alns.d;
-    B.sym = (const uint8_t *)c.r_sym.d;
-    B.is_exit = (const uint8_t *)c.r_is_exit.d;
+    B.nodes = (const replay::NodeRec *)c.r_nodes.d;
     B.queries = (const uint8_t *)c.queries.d;
-    B.dist_min = (const uint32_t *)c.r_dist_min.d;
-    B.dist_max = (const uint32_t *)c.r_dist_max.d;
-    B.succ_off = (const uint32_t *)c.r_succ_off.d;
     B.succ = (const uint32_t *)c.r_succ.d;
-    B.pred_off = (const uint32_t *)c.r_pred_off.d;
     B.pred = (const uint32_t *)c.r_pred.d;
-    B.bub_off = (const uint32_t *)c.r_bub_off.d;
     B.bub = (const uint32_t *)c.r_bub.d;
     B.path_off = (const uint32_t *)c.r_path_off.d;
     B.path_rem = (const uint32_t *)c.r_path_rem.d;
@@ -794,7 +779,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.prm = replay::Params{prm.mismatch, prm.gap_open, prm.gap_extend, prm.mode, prm.heuristic};
     B.slabs = (uint8_t *)c.r_slabs.d;
     B.slab_bytes = slab;
-    B.off_qhead = off_qhead, B.off_items = off_items, B.off_reached = off_reached, B.off_dfa = off_dfa;
+    B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_dfa = off_dfa;
     B.max_items = (uint32_t)max_items;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;

@@ -15,25 +15,26 @@
 //   backtrace              /root/reference/src/aligner/scoring/gap_affine.rs:550-657, 804-915
 //
 // Device mapping: the state machine is sequential per alignment, so one warp owns one alignment and
-// lane 0 drives it (10^4 families in flight = 10^4 warps); all mutable state lives in a per-warp
-// scratch slab in HBM laid out for single-transaction accesses:
-//   visited table   two-level: u32 block pointers per (node>>3, offset>>3), 8x8-cell blocks of
-//                   {M, D, I} u32 scores allocated on first touch (what the reference hashes)
-//   bucket queue    per priority three LIFO stacks threaded through a 16-byte item array
-//   reached sets    one bitmap row per node (the reference's BTreeSet<offset> per bubble exit)
+// lane 0 drives it (10^4 families in flight = 10^4 warps). A worker is bound by dependent DRAM misses
+// (measured: ~24k cycles per visited state with one array per attribute), so the layout is built to
+// need few of them:
+//   node record    32 B per node: successor / bubble list ranges, symbol, is-exit, distances to `end`,
+//                  predecessor range - one sector instead of seven arrays
+//   visited table  three dense planes (M, D, I) of V x W scores, u16 when every reachable score fits;
+//                  the top bit of a Match cell is the "reached" mark of the prune test (the reference's
+//                  BTreeSet<offset> per bubble exit), so marking costs no extra access and a prune
+//                  query reads flags and scores from the same cache lines; [lo, hi] bounds per node
+//                  keep the scans inside the occupied band
+//   bucket queue   three LIFO stacks per priority threaded through a 16-byte item array with a free
+//                  list; the heads of the 64 priorities around the current one live in shared memory
 // The same source compiles for the host (tests only) so the logic can be checked without a GPU.
 #pragma once
 #include <cstdint>
 
 #if defined(__CUDACC__)
 #define RP_HD __host__ __device__ __forceinline__
-#define RP_NI __host__ __device__ __forceinline__
 #else
 #define RP_HD inline
-#define RP_NI inline
-struct alignas(16) uint4 {
-    uint32_t x, y, z, w;
-};
 #endif
 
 // optional cycle accounting of the device build (-DRP_PROFILE): where a worker's time goes
@@ -52,30 +53,44 @@ constexpr uint32_t UNV = 0xFFFFFFFFu;  // Score::Unvisited
 enum : uint32_t { ST_M = 0, ST_D = 1, ST_I = 2 };
 enum : int { RP_OK = 0, RP_EMPTY_QUEUE = 1, RP_NO_BACKTRACE = 2, RP_SCORE_WRAP = 3, RP_OUT_OF_BLOCKS = 4, RP_OUT_OF_ITEMS = 5,
              RP_PRIORITY_RANGE = 6, RP_OUT_OF_PAIRS = 7 };
+constexpr uint32_t QWIN = 64;  // priorities whose stack heads are kept in the fast window
+
+struct alignas(16) NodeA {
+    uint32_t succ_off, bub_off;  // into Graph::succ / Graph::bub (quadruples)
+    uint32_t counts;             // n_succ | n_bub << 16
+    uint32_t symflags;           // symbol | is_exit << 8
+};
+struct alignas(16) NodeB {
+    uint32_t dist_min, dist_max;  // shortest / longest path length to `end`
+    uint32_t pred_off, n_pred;    // into Graph::pred
+};
+struct alignas(32) NodeRec {
+    NodeA a;
+    NodeB b;
+};
 
 struct Graph {  // node-id space, adjacency in the reference's order
     uint32_t V, start, end;
-    const uint32_t *succ_off, *succ, *pred_off, *pred;
-    const uint8_t *sym;
-    const uint32_t *dist_min, *dist_max;
-    const uint8_t *is_exit;
-    const uint32_t *bub_off, *bub;      // quadruples (exit, min_dist, max_dist, max(dist_min(exit), 1) - 1)
-    const uint32_t *path_off, *path_rem;  // may be null unless heuristic == 2
+    const NodeRec *nodes;
+    const uint32_t *succ, *pred;
+    const uint32_t *bub;                  // quadruples (exit, min_dist, max_dist, max(dist_min(exit), 1) - 1)
+    const uint32_t *path_off, *path_rem;  // sampled-path remainders for -H path (path_off has V + 1 entries)
 };
 
-struct Item {
+struct alignas(16) Item {
     uint32_t score, node, offset, next;
 };
 
 struct Scratch {  // one slab per in-flight alignment
-    void *planes;        // visited table: three dense planes (M, D, I) of V * W scores (u16 when every reachable score fits,
-                         // else u32), all-ones = unvisited; what the reference keeps in a hash of 8x8 blocks (gap_affine.rs:442-548)
-    uint32_t *qhead;     // f_max * 3 stack heads (0 = empty, else item index + 1)
-    Item *items;         // max_items
-    uint32_t *reached;   // V * rw bitmap words
-    uint32_t *dfa;       // (V + 2) * 3
+    void *planes;          // three planes (M, D, I) of V * W cells; cell = score | reached-flag (top bit); all-ones-but-top = unvisited
+    uint32_t *qhead;       // f_max * 3 stack heads (0 = empty, else item index + 1) - authoritative outside the window
+    uint32_t *qwin;        // QWIN * 3 heads of priorities [win_base, win_base + QWIN): shared memory on the device
+    Item *items;           // max_items
+    uint32_t *free_slots;  // max_items: stack of recycled item slots (its top stays cache-hot, unlike a list threaded through items)
+    uint32_t *rb;          // per node [lo, hi + 1] of the reached offsets (hi + 1 == 0: none)
+    uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
     uint64_t plane_elems;  // V * W
-    uint32_t W, rw, max_items, f_max;  // W = plane row stride; rw = reached row stride: bitmap words, then lo, then hi + 1 (0 = empty)
+    uint32_t W, max_items, f_max;
 };
 
 struct Params {
@@ -91,86 +106,64 @@ struct Result {
     uint32_t num_queued, num_visited, num_pruned;
 };
 
-// ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) as ONE out-of-line function -------------------
-// Called from two places of the state machine (popped states and greedily matched children); keeping a single copy of
-// this code keeps the kernel's instruction footprint small (instruction-fetch stalls were 1/3 of all stalls, profiles/).
-// Arguments travel by value in registers. Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped.
-template <typename CellT>
-struct PruneCtx {
-    const CellT *m_plane;     // Match-state scores, V * W
-    const uint32_t *reached;  // V rows of rw words: bitmap, lo, hi + 1
-    const uint32_t *bub;      // quadruples (exit, min_dist_to_exit, max_dist_to_exit, max(dist_min(exit), 1) - 1)
-    uint32_t W, rw, Q, o, e;
+template <typename CellT> struct CellTraits;
+template <> struct CellTraits<uint16_t> {
+    static constexpr uint16_t FLAG = 0x8000u, CUNV = 0x7FFFu;
+};
+template <> struct CellTraits<uint32_t> {
+    static constexpr uint32_t FLAG = 0x80000000u, CUNV = 0x7FFFFFFFu;
 };
 
-RP_HD uint32_t rp_hi_bit(uint32_t bits) {
-#if defined(__CUDA_ARCH__)
-    return 31 - __clz(bits);
-#else
-    return 31 - __builtin_clz(bits);
-#endif
-}
-RP_HD uint32_t rp_lo_bit(uint32_t bits) {
-#if defined(__CUDA_ARCH__)
-    return __ffs(bits) - 1;
-#else
-    return __builtin_ctz(bits);
-#endif
-}
-// largest member < lim, or UNV
-RP_HD uint32_t reached_prev(const uint32_t *row, uint32_t rw, uint32_t lim) {
-    const uint32_t lo = row[rw - 2], hi1 = row[rw - 1];
-    if (hi1 == 0 || lim <= lo) return UNV;
-    const uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
-    uint32_t w = i >> 5;
-    const uint32_t wlo = lo >> 5;
-    uint32_t bits = row[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
-    for (;;) {
-        if (bits) return w * 32 + rp_hi_bit(bits);
-        if (w == wlo) return UNV;
-        bits = row[--w];
-    }
-}
-// smallest member >= lim, or UNV
-RP_HD uint32_t reached_next(const uint32_t *row, uint32_t rw, uint32_t lim) {
-    const uint32_t lo = row[rw - 2], hi1 = row[rw - 1];
-    if (hi1 == 0 || lim >= hi1) return UNV;
-    const uint32_t i = lim < lo ? lo : lim;
-    uint32_t w = i >> 5;
-    const uint32_t whi = (hi1 - 1) >> 5;
-    uint32_t bits = row[w] & (0xFFFFFFFFu << (i & 31));
-    for (;;) {
-        if (bits) return w * 32 + rp_lo_bit(bits);
-        if (w == whi) return UNV;
-        bits = row[++w];
-    }
-}
+// ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) -----------------------------------------------
+// Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped (the reference would panic).
+template <typename CellT>
+struct PruneCtx {
+    const CellT *m_plane;  // Match plane, V * W
+    const uint32_t *rb;    // reached bounds per node
+    const uint32_t *bub;
+    uint32_t W, Q, o, e;
+};
 
 template <typename CellT>
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#endif
-int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
-    constexpr CellT CUNV = (CellT)~(CellT)0;
+RP_HD int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, uint32_t node, uint32_t off, uint32_t st,
+                     uint32_t score) {
+    constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
     bool wrapped = false;
     auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
     for (uint32_t k = bub_begin; k < bub_end; ++k) {
         const uint32_t exit = c.bub[4 * k], min_d = c.bub[4 * k + 1], max_d = c.bub[4 * k + 2], mde = c.bub[4 * k + 3];
-        const uint32_t *row = c.reached + (size_t)exit * c.rw;
-        if (row[c.rw - 1] == 0) continue;  // no offset reached at this exit yet: can improve
+        const uint32_t lo = c.rb[2 * exit], hi1 = c.rb[2 * exit + 1];
+        if (hi1 == 0) continue;  // no offset reached at this exit yet: can improve
         if (node == exit) continue;
         const uint32_t tmin = off + min_d, tmax = off + max_d;
         if (tmax > c.Q) continue;
         const CellT *mrow = c.m_plane + (size_t)exit * c.W;
+        // reached offsets = Match cells of the exit row with the flag bit; scans stay inside [lo, hi]
+        auto prev_of = [&](uint32_t lim) -> uint32_t {  // largest reached offset < lim
+            if (lim <= lo) return UNV;
+            uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
+            for (;;) {
+                if (mrow[i] & FLAG) return i;
+                if (i == lo) return UNV;
+                --i;
+            }
+        };
+        auto next_of = [&](uint32_t lim) -> uint32_t {  // smallest reached offset >= lim
+            if (lim >= hi1) return UNV;
+            uint32_t i = lim < lo ? lo : lim;
+            for (;;) {
+                if (mrow[i] & FLAG) return i;
+                if (++i >= hi1) return UNV;
+            }
+        };
         auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
-            const CellT v = mrow[r];
+            const CellT v = (CellT)(mrow[r] & (CellT)~FLAG);
             if (v == CUNV) wrapped = true;
             const uint32_t t = (uint32_t)v + plus;
             if (t == UNV) wrapped = true;
             return t;
         };
-        // reached.rs:191-255
-        auto improve_at = [&](uint32_t x, uint32_t left, uint32_t right) -> bool {
+        auto improve_at = [&](uint32_t x, uint32_t left, uint32_t right) -> bool {  // reached.rs:191-255
             uint32_t implicit;
             if (left != UNV && right != UNV) {
                 const uint32_t il = S(left, gap(x - left));
@@ -190,10 +183,10 @@ int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, ui
             return score < implicit;
         };
         bool can = false;
-        uint32_t prev = reached_prev(row, c.rw, tmin);
+        uint32_t prev = prev_of(tmin);
         bool have_last = false;
         uint32_t last = 0;
-        for (uint32_t nx = reached_next(row, c.rw, tmin); nx != UNV && nx <= tmax; nx = reached_next(row, c.rw, nx + 1)) {
+        for (uint32_t nx = next_of(tmin); nx != UNV && nx <= tmax; nx = next_of(nx + 1)) {
             const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
             if (st == ST_D && S(nx, c.o) > score) {
                 can = true;
@@ -219,7 +212,7 @@ int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, ui
             have_last = true;
         }
         if (!can) {
-            const uint32_t next = reached_next(row, c.rw, tmax == UNV ? tmax : tmax + 1);
+            const uint32_t next = next_of(tmax == UNV ? tmax : tmax + 1);
             if (!have_last && improve_at(tmin, prev, next)) can = true;
             else if ((!have_last || last < tmax) && improve_at(tmax, prev, next)) can = true;
             else if (prev != UNV && st == ST_I && S(prev, c.o) > score) can = true;
@@ -231,46 +224,49 @@ int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, ui
 }
 
 // CellT = uint16_t halves the table footprint (more alignments in flight); the host picks it only when the largest
-// possible score (every node deleted + every query base inserted) is below 0xFFFF.
+// possible score (every node deleted + every query base inserted) is below 0x7F00.
 template <typename CellT>
 struct Search {
-    static constexpr CellT CUNV = (CellT)~(CellT)0;
+    static constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
     const Graph &g;
     const uint8_t *q;
     const uint32_t Q;
     const Params &p;
     Scratch &s;
-    uint32_t n_items = 0, free_items = 0;
+    uint32_t n_items = 0, n_free = 0;  // bump pointer into the item arena; height of the recycled-slot stack
+    uint32_t f_cur = 0, f_hi = 0, win_base = 0;
+    bool q_empty = true;
+    int err = RP_OK;
 #if defined(RP_PROFILE)
     long long prof_prune = 0, prof_push = 0, prof_pop = 0;
     uint32_t prof_n_prune = 0;
-#endif  // free_items: LIFO list of popped item slots (index + 1)
-    uint32_t f_cur = 0, f_hi = 0;
-    bool q_empty = true;
-    int err = RP_OK;
+#endif
 
     RP_HD Search(const Graph &g_, const uint8_t *q_, uint32_t Q_, const Params &p_, Scratch &s_) : g(g_), q(q_), Q(Q_), p(p_), s(s_) {}
 
-    RP_HD bool sym_eq(uint32_t node, uint8_t c) const { return node == g.end || g.sym[node] == c; }
+    RP_HD NodeA node_a(uint32_t n) const { return g.nodes[n].a; }
+    RP_HD NodeB node_b(uint32_t n) const { return g.nodes[n].b; }
+    RP_HD bool sym_eq(uint32_t node, const NodeA &a, uint8_t c) const { return node == g.end || (a.symflags & 0xFF) == c; }
 
     // ---- visited table -------------------------------------------------------------------------
     RP_HD CellT *cell(uint32_t node, uint32_t off, uint32_t st) const {
         return static_cast<CellT *>(s.planes) + (size_t)st * s.plane_elems + (size_t)node * s.W + off;
     }
     RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
-        const CellT v = *cell(node, off, st);
+        const CellT v = (CellT)(*cell(node, off, st) & (CellT)~FLAG);
         return v == CUNV ? UNV : (uint32_t)v;
     }
     RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) { *cell(node, off, st) = (CellT)v; }
     RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
-        if (sizeof(CellT) == 2 && v >= 0xFFFFu) {  // cannot happen when the host sized CellT correctly
+        if (v >= (uint32_t)CUNV) {  // cannot happen when the host sized CellT correctly
             err = RP_SCORE_WRAP;
             return false;
         }
         CellT *c = cell(node, off, st);
         const CellT cur = *c;
-        if (cur == CUNV || v < (uint32_t)cur) {
-            *c = (CellT)v;
+        const CellT curv = (CellT)(cur & (CellT)~FLAG);
+        if (curv == CUNV || v < (uint32_t)curv) {
+            *c = (CellT)((CellT)v | (CellT)(cur & FLAG));  // a reached offset stays reached when its score improves
             return true;
         }
         return false;
@@ -293,12 +289,11 @@ struct Search {
         return (st == ST_M ? p.o : 0) + len * p.e;
     }
 
-    // ---- heuristic ----------------------------------------------------------------------------------
-    RP_HD uint32_t h(uint32_t node, uint32_t off, uint32_t st) const {
+    // ---- heuristic (dist = the node's distances to `end`) -----------------------------------------------
+    RP_HD uint32_t h(uint32_t node, uint32_t dist_min, uint32_t dist_max, uint32_t off, uint32_t st) const {
         if (p.heuristic == 0) return 0;
         if (p.heuristic == 1) {
-            const uint32_t a = g.dist_min[node], b = g.dist_max[node];
-            const uint32_t tmin = off + (a ? a - 1 : 0), tmax = off + (b ? b - 1 : 0);
+            const uint32_t tmin = off + (dist_min ? dist_min - 1 : 0), tmax = off + (dist_max ? dist_max - 1 : 0);
             if (tmin > Q) return gap_cost(st == ST_D ? ST_D : ST_M, tmin - Q);
             if (tmax < Q) return gap_cost(st == ST_I ? ST_I : ST_M, Q - tmax);
             return 0;
@@ -318,17 +313,30 @@ struct Search {
     }
 
     // ---- bucket queue ---------------------------------------------------------------------------------
-    RP_HD void push(uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+    RP_HD uint32_t *head_ptr(uint32_t f) const {
+        const uint32_t d = f - win_base;
+        return d < QWIN ? s.qwin + d * 3 : s.qhead + (size_t)f * 3;
+    }
+    RP_HD void move_window(uint32_t f) {  // make [f & ~63, +64) the fast window
+        const uint32_t nb = f & ~(QWIN - 1);
+        if (nb == win_base) return;
+        for (uint32_t i = 0; i < QWIN * 3; ++i) {
+            const uint32_t fo = win_base * 3 + i, fn = nb * 3 + i;
+            if (fo < s.f_max * 3) s.qhead[fo] = s.qwin[i];
+            s.qwin[i] = fn < s.f_max * 3 ? s.qhead[fn] : 0;
+        }
+        win_base = nb;
+    }
+    RP_HD void push(uint32_t node, uint32_t dist_min, uint32_t dist_max, uint32_t off, uint32_t st, uint32_t score) {
         RP_T0;
-        const uint32_t f = score + h(node, off, st);
+        const uint32_t f = score + h(node, dist_min, dist_max, off, st);
         if (f >= s.f_max) {
             err = RP_PRIORITY_RANGE;
             return;
         }
         uint32_t slot;
-        if (free_items) {
-            slot = free_items - 1;
-            free_items = s.items[slot].next;
+        if (n_free) {
+            slot = s.free_slots[--n_free];
         } else {
             if (n_items >= s.max_items) {
                 err = RP_OUT_OF_ITEMS;
@@ -336,7 +344,7 @@ struct Search {
             }
             slot = n_items++;
         }
-        uint32_t *head = s.qhead + (size_t)f * 3 + st;
+        uint32_t *head = head_ptr(f) + st;
         s.items[slot] = Item{score, node, off, *head};
         *head = slot + 1;
         if (q_empty) {
@@ -351,14 +359,14 @@ struct Search {
     RP_HD bool pop(Item &out, uint32_t &st) {
         if (q_empty) return false;
         for (;;) {
-            uint32_t *head = s.qhead + (size_t)f_cur * 3;
+            if (f_cur - win_base >= QWIN) move_window(f_cur);
+            uint32_t *head = head_ptr(f_cur);
             for (uint32_t k = 0; k < 3; ++k) {  // Match, then Deletion, then Insertion
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
                     head[k] = out.next;
-                    s.items[slot].next = free_items;
-                    free_items = slot + 1;
+                    s.free_slots[n_free++] = slot;
                     st = k;
                     return true;
                 }
@@ -371,13 +379,11 @@ struct Search {
         }
     }
 
-    // ---- reached sets (BTreeSet<offset> per exit) --------------------------------------------------------
-    // Row = bitmap words followed by [lo, hi + 1] of the members so range queries never scan outside the occupied band.
-    RP_HD void mark_reached(uint32_t node, uint32_t off, uint32_t st) {
-        if (st == ST_M && g.is_exit[node]) {
-            uint32_t *row = s.reached + (size_t)node * s.rw;
-            row[off >> 5] |= 1u << (off & 31);
-            uint32_t *b = row + (s.rw - 2);
+    // ---- reached marks (BTreeSet<offset> per exit; gap_affine.rs:767-773) -------------------------------
+    RP_HD void mark_reached(uint32_t node, bool is_exit, uint32_t off, uint32_t st) {
+        if (st == ST_M && is_exit) {
+            *cell(node, off, ST_M) |= FLAG;
+            uint32_t *b = s.rb + 2 * (size_t)node;
             if (b[1] == 0) {
                 b[0] = off, b[1] = off + 1;
             } else {
@@ -386,12 +392,13 @@ struct Search {
             }
         }
     }
-    RP_HD bool prune(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
+
+    RP_HD bool prune(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
+        const uint32_t nb = a.counts >> 16;
+        if (nb == 0) return false;
         RP_T0;
-        const uint32_t b = g.bub_off[node], e = g.bub_off[node + 1];
-        if (b == e) return false;
-        PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.reached, g.bub, s.W, s.rw, Q, p.o, p.e};
-        const int r = prune_eval<CellT>(c, b, e, node, off, st, score);
+        PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, g.bub, s.W, Q, p.o, p.e};
+        const int r = prune_eval<CellT>(c, a.bub_off, a.bub_off + nb, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
         RP_ACC(prof_prune);
 #if defined(RP_PROFILE)
@@ -406,15 +413,16 @@ struct Search {
     }
 
     // ---- backtrace (gap_affine.rs:550-657) ------------------------------------------------------------------
-    RP_NI bool bt(uint32_t node, uint32_t off, uint32_t st, uint32_t &bn, uint32_t &bo, uint32_t &bs) {
+    RP_HD bool bt(uint32_t node, uint32_t off, uint32_t st, uint32_t &bn, uint32_t &bo, uint32_t &bs) {
         const uint32_t cur = get(node, off, st);
         if (cur == UNV) return false;
+        const NodeB nb = node_b(node);
         if (st == ST_M) {
             if (off > 0) {
-                const bool me = sym_eq(node, q[off - 1]) || node == g.end;
+                const bool me = sym_eq(node, node_a(node), q[off - 1]) || node == g.end;
                 const uint32_t po = node == g.end ? off : off - 1;
                 const uint32_t want = me ? cur : sub(cur, p.x);
-                for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+                for (uint32_t k = nb.pred_off; k < nb.pred_off + nb.n_pred; ++k)
                     if (get(g.pred[k], po, ST_M) == want) {
                         bn = g.pred[k], bo = po, bs = ST_M;
                         return true;
@@ -430,12 +438,12 @@ struct Search {
             }
         } else if (st == ST_D) {
             const uint32_t w1 = sub(sub(cur, p.o), p.e), w2 = sub(cur, p.e);
-            for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+            for (uint32_t k = nb.pred_off; k < nb.pred_off + nb.n_pred; ++k)
                 if (get(g.pred[k], off, ST_M) == w1) {
                     bn = g.pred[k], bo = off, bs = ST_M;
                     return true;
                 }
-            for (uint32_t k = g.pred_off[node]; k < g.pred_off[node + 1]; ++k)
+            for (uint32_t k = nb.pred_off; k < nb.pred_off + nb.n_pred; ++k)
                 if (get(g.pred[k], off, ST_D) == w2) {
                     bn = g.pred[k], bo = off, bs = ST_D;
                     return true;
@@ -452,25 +460,23 @@ struct Search {
     // The whole alignment (astar.rs:108-226 + mod.rs:114-145 non-empty graph).
     RP_HD Result run(uint32_t *out_r, uint32_t *out_q, uint32_t cap) {
         Result res{0, 0, RP_OK, 0, 0, 0};
-        const uint32_t oe = p.o + p.e, oe8 = (p.o + p.e) & 0xFF;  // the queued delta is a u8 sum in the reference
-        if (p.mode == 0) {
-            push(g.start, 0, ST_M, 0);
-            set(g.start, 0, ST_M, 0);
+        const uint32_t oe8 = (p.o + p.e) & 0xFF;  // the queued delta is a u8 sum in the reference (gap_affine.rs:288)
+        auto push_initial = [&](uint32_t n) {
+            const NodeB b = node_b(n);
+            push(n, b.dist_min, b.dist_max, 0, ST_M, 0);
+            set(n, 0, ST_M, 0);
             ++res.num_queued;
+        };
+        if (p.mode == 0) {
+            push_initial(g.start);
         } else {
             bool any = false;
             for (uint32_t n = g.V; n-- > 0;)
                 if (n != g.start && n != g.end) {
-                    push(n, 0, ST_M, 0);
-                    set(n, 0, ST_M, 0);
-                    ++res.num_queued;
+                    push_initial(n);
                     any = true;
                 }
-            if (!any) {
-                push(g.start, 0, ST_M, 0);
-                set(g.start, 0, ST_M, 0);
-                ++res.num_queued;
-            }
+            if (!any) push_initial(g.start);
         }
         uint32_t end_score = 0, end_node = 0, end_off = 0;
         bool done = false;
@@ -487,40 +493,44 @@ struct Search {
                 end_score = it.score, end_node = it.node, end_off = it.offset;
                 break;
             }
-            if (prune(it.score, it.node, it.offset, st)) {
+            const NodeA na = node_a(it.node);
+            const NodeB nb = node_b(it.node);
+            if (prune(it.score, it.node, na, it.offset, st)) {
                 ++res.num_pruned;
                 continue;
             }
-            mark_reached(it.node, it.offset, st);
+            mark_reached(it.node, (na.symflags >> 8) & 1, it.offset, st);
             ++res.num_visited;
             const uint32_t score = it.score;
             if (st == ST_M) {
-                // depth-first greedy match extension (dfa.rs:138-250); frames = (node, offset, next successor slot)
+                // depth-first greedy match extension (dfa.rs:138-250)
                 uint32_t depth = 1;
                 uint32_t *F = s.dfa;
-                F[0] = it.node, F[1] = it.offset, F[2] = g.succ_off[it.node];
+                F[0] = it.node, F[1] = it.offset, F[2] = na.succ_off, F[3] = na.succ_off + (na.counts & 0xFFFF);
+                F[4] = nb.dist_min, F[5] = nb.dist_max;
                 uint32_t dfa_visited = 0;
                 while (depth > 0 && err == RP_OK) {
                     // offset-0 special case, evaluated on every resume while a single frame is on the stack (dfa.rs:145-168)
                     bool virtual_end = false;
                     uint32_t v_parent = 0;
-                    if (depth == 1 && Q != 0 && F[1] == 0 && sym_eq(F[0], q[0])) {
+                    if (depth == 1 && Q != 0 && F[1] == 0 && sym_eq(F[0], na, q[0])) {
                         if (relax(F[0], 1, ST_M, score)) {
                             v_parent = F[0];
-                            F[1] = 1, F[2] = g.succ_off[F[0]];
-                            mark_reached(F[0], 1, ST_M);
+                            F[1] = 1, F[2] = na.succ_off;
+                            mark_reached(F[0], (na.symflags >> 8) & 1, 1, ST_M);
                             ++dfa_visited;
                             if (Q == 1) virtual_end = true;
                         }
                     }
                     int kind = 0;  // 0 exhausted, 1 ref-graph end, 2 query end, 3 match, 4 mismatch
-                    uint32_t pn, po, cn = 0, co = 0;
+                    uint32_t pn, po, pdmin, pdmax, cn = 0, co = 0;
+                    NodeA ca{0, 0, 0, 0};
+                    uint32_t *fr = F + (size_t)(depth - 1) * 6;
+                    pn = fr[0], po = fr[1], pdmin = fr[4], pdmax = fr[5];
                     if (virtual_end) {
                         kind = 1, pn = v_parent, po = 0, cn = v_parent, co = 1;
                     } else {
-                        uint32_t *fr = F + (size_t)(depth - 1) * 3;
-                        pn = fr[0], po = fr[1];
-                        const uint32_t se = g.succ_off[pn + 1];
+                        const uint32_t se = fr[3];
                         while (fr[2] < se) {
                             const uint32_t child = g.succ[fr[2]++];
                             if (child == g.end) {
@@ -532,7 +542,8 @@ struct Search {
                                 kind = 2, cn = child;
                                 break;
                             }
-                            if (sym_eq(child, q[po])) {
+                            ca = node_a(child);
+                            if ((ca.symflags & 0xFF) == q[po]) {
                                 if (relax(child, po + 1, ST_M, score)) {
                                     kind = 3, cn = child, co = po + 1;
                                     break;
@@ -546,11 +557,13 @@ struct Search {
                     if (kind == 0) {
                         --depth;
                     } else if (kind == 3) {
-                        if (prune(score, cn, co, ST_M)) continue;
-                        mark_reached(cn, co, ST_M);
+                        if (prune(score, cn, ca, co, ST_M)) continue;
+                        mark_reached(cn, (ca.symflags >> 8) & 1, co, ST_M);
                         ++dfa_visited;
-                        uint32_t *nf = F + (size_t)depth * 3;
-                        nf[0] = cn, nf[1] = co, nf[2] = g.succ_off[cn];
+                        const NodeB cb = node_b(cn);
+                        uint32_t *nf = F + (size_t)depth * 6;
+                        nf[0] = cn, nf[1] = co, nf[2] = ca.succ_off, nf[3] = ca.succ_off + (ca.counts & 0xFFFF);
+                        nf[4] = cb.dist_min, nf[5] = cb.dist_max;
                         ++depth;
                     } else if (kind == 1) {
                         if (is_end(cn, co, ST_M)) {
@@ -559,26 +572,28 @@ struct Search {
                             break;
                         }
                         if (relax(pn, po + 1, ST_I, add(add(score, p.o), p.e))) {  // gap_affine.rs:346-367
-                            push(pn, po + 1, ST_I, add(score, oe8));
+                            push(pn, pdmin, pdmax, po + 1, ST_I, add(score, oe8));
                             ++res.num_queued;
                         }
                     } else if (kind == 2) {
                         if (relax(cn, po, ST_D, add(add(score, p.o), p.e))) {  // gap_affine.rs:369-391
-                            push(cn, po, ST_D, add(score, oe8));
+                            const NodeB cb = node_b(cn);
+                            push(cn, cb.dist_min, cb.dist_max, po, ST_D, add(score, oe8));
                             ++res.num_queued;
                         }
                     } else {  // mismatch: gap_affine.rs:393-430
+                        const NodeB cb = node_b(cn);
                         if (relax(cn, co, ST_M, add(score, p.x))) {
-                            push(cn, co, ST_M, add(score, p.x));
+                            push(cn, cb.dist_min, cb.dist_max, co, ST_M, add(score, p.x));
                             ++res.num_queued;
                         }
                         const uint32_t ns = add(add(score, p.o), p.e);
                         if (relax(pn, po + 1, ST_I, ns)) {
-                            push(pn, po + 1, ST_I, add(score, oe8));
+                            push(pn, pdmin, pdmax, po + 1, ST_I, add(score, oe8));
                             ++res.num_queued;
                         }
                         if (relax(cn, po, ST_D, ns)) {
-                            push(cn, po, ST_D, add(score, oe8));
+                            push(cn, cb.dist_min, cb.dist_max, po, ST_D, add(score, oe8));
                             ++res.num_queued;
                         }
                     }
@@ -586,26 +601,29 @@ struct Search {
                 if (!done) res.num_visited += dfa_visited;
             } else if (st == ST_I) {  // gap_affine.rs:307-322
                 if (relax(it.node, it.offset, ST_M, score)) {
-                    push(it.node, it.offset, ST_M, score);
+                    push(it.node, nb.dist_min, nb.dist_max, it.offset, ST_M, score);
                     ++res.num_queued;
                 }
                 if (it.offset < Q && relax(it.node, it.offset + 1, ST_I, add(score, p.e))) {
-                    push(it.node, it.offset + 1, ST_I, add(score, p.e));
+                    push(it.node, nb.dist_min, nb.dist_max, it.offset + 1, ST_I, add(score, p.e));
                     ++res.num_queued;
                 }
             } else {  // gap_affine.rs:323-341
                 if (relax(it.node, it.offset, ST_M, score)) {
-                    push(it.node, it.offset, ST_M, score);
+                    push(it.node, nb.dist_min, nb.dist_max, it.offset, ST_M, score);
                     ++res.num_queued;
                 }
-                for (uint32_t k = g.succ_off[it.node]; k < g.succ_off[it.node + 1]; ++k)
-                    if (relax(g.succ[k], it.offset, ST_D, add(score, p.e))) {
-                        push(g.succ[k], it.offset, ST_D, add(score, p.e));
+                const uint32_t se = na.succ_off + (na.counts & 0xFFFF);
+                for (uint32_t k = na.succ_off; k < se; ++k) {
+                    const uint32_t c = g.succ[k];
+                    if (relax(c, it.offset, ST_D, add(score, p.e))) {
+                        const NodeB cb = node_b(c);
+                        push(c, cb.dist_min, cb.dist_max, it.offset, ST_D, add(score, p.e));
                         ++res.num_queued;
                     }
+                }
             }
         }
-        (void)oe;
         res.score = end_score;
         if (err != RP_OK) {
             res.status = err;
@@ -614,7 +632,7 @@ struct Search {
         // backtrace (gap_affine.rs:804-915), pairs written backwards from out[cap-1]
         uint32_t pos = cap;
         if (Q == 0) {
-        } else if (Q == 1 && end_off == 1 && sym_eq(end_node, q[0])) {
+        } else if (Q == 1 && end_off == 1 && sym_eq(end_node, node_a(end_node), q[0])) {
             out_r[--pos] = end_node;
             out_q[pos] = 0;
         } else {
@@ -658,13 +676,13 @@ struct Search {
 
 // scratch sizing shared by host and device code
 struct ScratchDims {
-    uint32_t W, rw, f_max;
+    uint32_t W, f_max;
     RP_HD ScratchDims(uint32_t V, uint32_t Q, uint32_t x, uint32_t o, uint32_t e) {
-        W = (Q + 2 + 7) & ~7u;  // offsets 0..Q (+1: the reference relaxes I(v, Q+1) in one corner case, gap_affine.rs:360)
-        rw = (Q + 1 + 31) / 32 + 2;  // + 2: [lo, hi + 1] of the row's members
+        W = (Q + 2 + 7) & ~7u;  // offsets 0..Q with slack; multiple of 8 cells keeps rows 16-byte aligned
         uint32_t m = x > o + e ? x : o + e;
         if (m == 0) m = 1;
         f_max = (V + Q + 4) * m + o + 64;  // any score and any gap-cost heuristic value stays below this
+        f_max = (f_max + QWIN - 1) & ~(QWIN - 1);
     }
 };
 

@@ -12,24 +12,25 @@ namespace poasta {
 
 struct RGraphDesc {
     uint32_t V, start, end;
-    uint32_t node_base;     // sym, dist_min, dist_max, is_exit
-    uint32_t succoff_base, predoff_base, buboff_base, pathoff_base;  // each V + 1 entries, values relative to *_base below
-    uint32_t succ_base, pred_base, bub_base, path_base;
+    uint32_t node_base;                                  // into nodes (NodeRec) ; path_off uses node_base + graph index slack
+    uint32_t succ_base, pred_base, bub_base, path_base;  // bases of this graph's succ / pred / bub (quadruples) / path_rem
+    uint32_t pathoff_base;                               // V + 1 entries
 };
 
 struct ReplayDev {
     const RGraphDesc *graphs;
     const AlnDesc *alns;
-    const uint8_t *sym, *is_exit, *queries;
-    const uint32_t *dist_min, *dist_max, *succ_off, *succ, *pred_off, *pred, *bub_off, *bub, *path_off, *path_rem;
+    const replay::NodeRec *nodes;
+    const uint8_t *queries;
+    const uint32_t *succ, *pred, *bub, *path_off, *path_rem;
     uint32_t n_alns;
     replay::Params prm;
     uint8_t *slabs;
-    uint64_t slab_bytes, off_qhead, off_items, off_reached, off_dfa;  // byte offsets inside a slab (score planes at 0)
+    uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_dfa;  // byte offsets inside a slab (score planes at 0)
     uint32_t max_items;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
-    uint32_t *stats;  // per alignment: queued, visited, pruned, blocks
+    uint32_t *stats;  // per alignment: queued, visited, pruned, item high-water mark
 };
 
 constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few workers over all SMs; 2 reaches 64 warps/SM
@@ -38,8 +39,9 @@ constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few worke
 // but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
 template <typename CellT, int MINB>
 __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];  // queue-head window of each worker
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
     for (;;) {
         uint32_t a = 0;
@@ -49,33 +51,28 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
         const AlnDesc ad = B.alns[a];
         const RGraphDesc gd = B.graphs[ad.graph];
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
-        // reset the slab for THIS alignment with 128-bit stores: score planes to all-ones (unvisited), bucket heads and
-        // reached bitmaps to zero
+        // reset the slab for THIS alignment with 128-bit stores: score planes to "unvisited", bucket heads and reached bounds to 0
         {
-            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), z = make_uint4(0, 0, 0, 0);
+            const uint32_t pat = sizeof(CellT) == 2 ? 0x7FFF7FFFu : 0x7FFFFFFFu;
+            const uint4 unv = make_uint4(pat, pat, pat, pat), z = make_uint4(0, 0, 0, 0);
             uint4 *p0 = reinterpret_cast<uint4 *>(slab);
             const uint64_t n0 = ((uint64_t)3 * gd.V * dims.W * sizeof(CellT) + 15) / 16;
-            for (uint64_t i = lane; i < n0; i += 32) p0[i] = ones;
+            for (uint64_t i = lane; i < n0; i += 32) p0[i] = unv;
             uint4 *p1 = reinterpret_cast<uint4 *>(slab + B.off_qhead);
             const uint32_t n1 = ((uint64_t)dims.f_max * 3 + 3) / 4;
             for (uint32_t i = lane; i < n1; i += 32) p1[i] = z;
-            uint4 *p2 = reinterpret_cast<uint4 *>(slab + B.off_reached);
-            const uint32_t n2 = ((uint64_t)gd.V * dims.rw + 3) / 4;
+            uint4 *p2 = reinterpret_cast<uint4 *>(slab + B.off_rb);
+            const uint32_t n2 = ((uint64_t)gd.V * 2 + 3) / 4;
             for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
+            for (uint32_t i = lane; i < replay::QWIN * 3; i += 32) s_qwin[wib][i] = 0;
         }
         __syncwarp();
         if (lane == 0) {
             replay::Graph g;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
-            g.succ_off = B.succ_off + gd.succoff_base;
+            g.nodes = B.nodes + gd.node_base;
             g.succ = B.succ + gd.succ_base;
-            g.pred_off = B.pred_off + gd.predoff_base;
             g.pred = B.pred + gd.pred_base;
-            g.sym = B.sym + gd.node_base;
-            g.dist_min = B.dist_min + gd.node_base;
-            g.dist_max = B.dist_max + gd.node_base;
-            g.is_exit = B.is_exit + gd.node_base;
-            g.bub_off = B.bub_off + gd.buboff_base;
             g.bub = B.bub + (uint64_t)gd.bub_base * 4;
             g.path_off = B.path_off + gd.pathoff_base;
             g.path_rem = B.path_rem + gd.path_base;
@@ -83,10 +80,12 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             s.planes = slab;
             s.plane_elems = (uint64_t)gd.V * dims.W;
             s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
+            s.qwin = s_qwin[wib];
             s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
-            s.reached = reinterpret_cast<uint32_t *>(slab + B.off_reached);
+            s.free_slots = reinterpret_cast<uint32_t *>(slab + B.off_free);
+            s.rb = reinterpret_cast<uint32_t *>(slab + B.off_rb);
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
-            s.W = dims.W, s.rw = dims.rw, s.f_max = dims.f_max;
+            s.W = dims.W, s.f_max = dims.f_max;
             s.max_items = B.max_items;
 #if defined(RP_PROFILE)
             const long long t_begin = clock64();
@@ -100,7 +99,6 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             B.stats[4 * a + 3] = search.n_items;
 #if defined(RP_PROFILE)
             {
-                static_assert(true, "");
                 const long long total = clock64() - t_begin;
                 if (a < 8)
                     printf("aln %u: total %lld cyc, prune %lld (%.1f%%, %u calls, %lld cyc/call), push %lld (%.1f%%), visited %u queued %u pruned %u -> %lld cyc/visit\n",
@@ -118,15 +116,15 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
 struct PackedReplay {
     std::vector<RGraphDesc> graphs;
     std::vector<AlnDesc> alns;
-    std::vector<uint8_t> sym, is_exit, queries;
-    std::vector<uint32_t> dist_min, dist_max, succ_off, succ, pred_off, pred, bub_off, bub, path_off, path_rem;
+    std::vector<replay::NodeRec> nodes;
+    std::vector<uint8_t> queries;
+    std::vector<uint32_t> succ, pred, bub, path_off, path_rem;
     uint64_t out_elems = 0, total_cells = 0;
     uint32_t max_V = 0, max_Q = 0;
 
     void clear() {
-        graphs.clear(), alns.clear(), sym.clear(), is_exit.clear(), queries.clear();
-        dist_min.clear(), dist_max.clear(), succ_off.clear(), succ.clear(), pred_off.clear(), pred.clear();
-        bub_off.clear(), bub.clear(), path_off.clear(), path_rem.clear();
+        graphs.clear(), alns.clear(), nodes.clear(), queries.clear();
+        succ.clear(), pred.clear(), bub.clear(), path_off.clear(), path_rem.clear();
         out_elems = total_cells = 0;
         max_V = max_Q = 0;
     }
@@ -135,24 +133,15 @@ struct PackedReplay {
         RGraphDesc gd;
         const uint32_t V = v.n_nodes;
         gd.V = V, gd.start = v.start_node, gd.end = v.end_node;
-        gd.node_base = (uint32_t)sym.size();
-        gd.succoff_base = (uint32_t)succ_off.size();
-        gd.predoff_base = (uint32_t)pred_off.size();
-        gd.buboff_base = (uint32_t)bub_off.size();
-        gd.pathoff_base = (uint32_t)path_off.size();
+        gd.node_base = (uint32_t)nodes.size();
         gd.succ_base = (uint32_t)succ.size();
         gd.pred_base = (uint32_t)pred.size();
         gd.bub_base = (uint32_t)(bub.size() / 4);
         gd.path_base = (uint32_t)path_rem.size();
-        sym.insert(sym.end(), v.symbol, v.symbol + V);
-        is_exit.insert(is_exit.end(), si.is_exit.begin(), si.is_exit.end());
-        dist_min.insert(dist_min.end(), si.dist_min.begin(), si.dist_min.end());
-        dist_max.insert(dist_max.end(), si.dist_max.begin(), si.dist_max.end());
-        succ_off.insert(succ_off.end(), v.succ_off, v.succ_off + V + 1);
+        gd.pathoff_base = (uint32_t)path_off.size();
+        si.node_records(v, nodes);
         succ.insert(succ.end(), v.succ, v.succ + v.succ_off[V]);
-        pred_off.insert(pred_off.end(), v.pred_off, v.pred_off + V + 1);
         pred.insert(pred.end(), v.pred, v.pred + v.pred_off[V]);
-        bub_off.insert(bub_off.end(), si.bub_off.begin(), si.bub_off.end());
         bub.insert(bub.end(), si.bub.begin(), si.bub.end());
         if (si.path_off.empty()) {
             path_off.insert(path_off.end(), V + 1, 0u);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/poasta_b200.h"
+#include "replay_core.hpp"
 
 namespace poasta {
 
@@ -22,6 +23,22 @@ struct SearchIndex {
     std::vector<uint32_t> bub;      // quadruples (exit, min_dist_to_exit, max_dist_to_exit, max(dist_min(exit), 1) - 1)
     std::vector<uint32_t> path_off;  // V + 1 (only when the path heuristic is requested)
     std::vector<uint32_t> path_rem;  // remaining path length for the first <= 5 sampled paths through a node
+
+    // 32-byte node records of the search kernel (replay_core.hpp); offsets are relative to the graph's own arrays
+    void node_records(const poasta_graph_view &v, std::vector<replay::NodeRec> &out) const {
+        for (uint32_t n = 0; n < v.n_nodes; ++n) {
+            replay::NodeRec r;
+            r.a.succ_off = v.succ_off[n];
+            r.a.bub_off = bub_off[n];
+            r.a.counts = (v.succ_off[n + 1] - v.succ_off[n]) | ((bub_off[n + 1] - bub_off[n]) << 16);
+            r.a.symflags = (uint32_t)v.symbol[n] | ((uint32_t)is_exit[n] << 8);
+            r.b.dist_min = dist_min[n];
+            r.b.dist_max = dist_max[n];
+            r.b.pred_off = v.pred_off[n];
+            r.b.n_pred = v.pred_off[n + 1] - v.pred_off[n];
+            out.push_back(r);
+        }
+    }
 
     struct G {
         const poasta_graph_view &v;
