@@ -229,6 +229,9 @@ def main():
         # roofline of the dominant kernel of the step (by device time)
         dominant = "replay_kernel (order-exact search)" if search_ms > dp_ms else "dp_fill kernels"
         dom_ms = max(search_ms, dp_ms)
+        # kernel durations are summed over the concurrent pipeline lanes, so the sum can exceed the wall clock of the
+        # timed region: the dominant kernel cannot have been busy longer than that
+        dom_ms = min(dom_ms, wall_max * 1e3)
         achieved = per_rank_cells * ALG_BYTES_PER_CU / (dom_ms / 1e3) / 1e9
         tr = measured_traffic().get("replay_kernel" if search_ms > dp_ms else "dp_fill_warp_kernel")
         n_dom_launches = max(1, int(launches / world) // (3 if tiebreak == TIEBREAK_EXACT else 4))
