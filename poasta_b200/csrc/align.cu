@@ -42,7 +42,7 @@ struct BatchDev {
     const GraphDesc *graphs;
     const AlnDesc *alns;
     const uint8_t *node_sym;
-    const uint32_t *node_info, *node_id, *pred_off, *pred_rank, *pred_slot;
+    const uint32_t *node_info, *node_id, *ord_slot, *pred_off, *pred_rank, *pred_slot;
     const uint8_t *queries;
     uint32_t n_alns;
     int x, oe, e;
@@ -417,7 +417,7 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sms = 0;
-    Buf graphs, alns, node_sym, node_info, node_id, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
+    Buf graphs, alns, node_sym, node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
     Buf r_graphs, r_nodes, r_succ, r_pred, r_bub, r_path_off, r_path_rem, r_slabs, r_stats;
@@ -491,23 +491,23 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     cudaMemGetInfo(&free_b, &total_b);
     // warp-per-alignment kernel when every query fits 32 lanes x 32 columns, else the CTA-per-alignment kernel
     static const bool force_cta = getenv("POASTA_DP_KERNEL") && !strcmp(getenv("POASTA_DP_KERNEL"), "cta");
-    const bool use_warp = pb.max_W <= (uint32_t)WARP_MAX_W && !force_cta;
+    const bool use_warp = pb.max_W <= (uint32_t)WARP_MAX_W && pb.max_in_degree <= 1023 && !force_cta;
     const size_t per_slot = use_warp ? (size_t)pb.max_store_cells * 2 * sizeof(int) : (size_t)pb.max_cells * 2 * sizeof(int);
     size_t slots = (size_t)c.n_sms * 4;  // CTA slots of the CTA-per-alignment kernel
     if (use_warp) {                      // warp slots: what the register file lets be resident
         int ctas = 0;
-        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint16_t, false>, WARP_KERNEL_WARPS * 32, 0);
-        else if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint32_t, true>, WARP_KERNEL_WARPS * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<uint16_t, true>, WARP_KERNEL_WARPS * 32, 0);
+        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<false>, WARP_KERNEL_WARPS * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<true>, WARP_KERNEL_WARPS * 32, 0);
         slots = (size_t)c.n_sms * std::max(1, ctas) * WARP_KERNEL_WARPS;
     }
     slots = std::min<size_t>(slots, use_warp ? ((size_t)n + 3) / 4 * 4 : n);
     const size_t scratch_budget = std::max<size_t>(((size_t)8 << 30) / tl_lane_count, c.scratch.cap);
     while (slots > 4 && slots * per_slot > scratch_budget) slots = std::max<size_t>(4, slots / 2 / 4 * 4);
-    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve((scores_only && use_warp) ? 16 : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
+    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(use_warp ? (scores_only ? 16 : pb.ptrace_words * 4) : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
-              c.node_id.reserve(pb.node_id.size() * 4) && c.pred_off.reserve(pb.pred_off.size() * 4) &&
+              c.node_id.reserve(pb.node_id.size() * 4) && c.ord_slot.reserve(pb.ord_slot.size() * 4) &&
+              c.pred_off.reserve(pb.pred_off.size() * 4) &&
               c.pred_rank.reserve(pb.pred_rank.size() * 4 + 4) && c.pred_slot.reserve(pb.pred_slot.size() * 4 + 4) &&
               c.queries.reserve(pb.queries.size() + 4) &&
               c.scores.reserve(n * 4) && c.counter.reserve(4) && c.out_r.reserve(pb.out_elems * 4) &&
@@ -520,6 +520,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaMemcpyAsync(c.node_sym.d, pb.node_sym.data(), pb.node_sym.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.node_info.d, pb.node_info.data(), pb.node_info.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.node_id.d, pb.node_id.data(), pb.node_id.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c.ord_slot.d, pb.ord_slot.data(), pb.ord_slot.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.pred_off.d, pb.pred_off.data(), pb.pred_off.size() * 4, cudaMemcpyHostToDevice, s));
     if (!pb.pred_rank.empty()) {
         CK(cudaMemcpyAsync(c.pred_rank.d, pb.pred_rank.data(), pb.pred_rank.size() * 4, cudaMemcpyHostToDevice, s));
@@ -537,6 +538,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.node_sym = (const uint8_t *)c.node_sym.d;
     P.node_info = (const uint32_t *)c.node_info.d;
     P.node_id = (const uint32_t *)c.node_id.d;
+    P.ord_slot = (const uint32_t *)c.ord_slot.d;
     P.pred_off = (const uint32_t *)c.pred_off.d;
     P.pred_rank = (const uint32_t *)c.pred_rank.d;
     P.pred_slot = (const uint32_t *)c.pred_slot.d;
@@ -558,9 +560,8 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaEventRecord(c.ev0, s));
     if (use_warp) {
         const unsigned grid = (unsigned)(slots / WARP_KERNEL_WARPS), block = WARP_KERNEL_WARPS * 32;
-        if (scores_only) dp_fill_warp_kernel<uint16_t, false><<<grid, block, 0, s>>>(P);
-        else if (wide) dp_fill_warp_kernel<uint32_t, true><<<grid, block, 0, s>>>(P);
-        else dp_fill_warp_kernel<uint16_t, true><<<grid, block, 0, s>>>(P);
+        if (scores_only) dp_fill_warp_kernel<false><<<grid, block, 0, s>>>(P);
+        else dp_fill_warp_kernel<true><<<grid, block, 0, s>>>(P);
     } else {
         if (wide) dp_fill_kernel<uint32_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
         else dp_fill_kernel<uint16_t><<<(unsigned)slots, FILL_THREADS, 0, s>>>(P);
@@ -587,7 +588,8 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         return 0;
     }
     const unsigned tb_blocks = (n + 127) / 128;
-    if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
+    if (use_warp) traceback_planes_kernel<<<tb_blocks, 128, 0, s>>>(P);
+    else if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
     else traceback_kernel<uint16_t><<<tb_blocks, 128, 0, s>>>(P);
     scan_kernel<<<1, 1024, 0, s>>>(P.n_pairs, (uint32_t *)c.offsets.d, n);
     CK(cudaEventRecord(c.ev1, s));
@@ -669,7 +671,7 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
                 continue;
             }
             const uint64_t add = V * ((p.qlen + 4) & ~3ull) * 4;
-            if (!pb.alns.empty() && (pb.trace_elems * 4 + add > budget || pb.alns.size() >= (1u << 20))) break;
+            if (!pb.alns.empty() && (pb.trace_elems * 2 + add > budget || pb.alns.size() >= (1u << 20))) break;
             if (p.graph_key != last_key || pb.graphs.empty()) {
                 last_gid = pb.add_graph(*p.graph, rank_scratch);
                 last_key = p.graph_key;

@@ -27,6 +27,7 @@ struct GraphDesc {
     uint32_t predoff_base;  // into pred_off (V + 1 entries)
     uint32_t max_in_degree;
     uint32_t n_stored;      // rows that later rows read from the row store (warp kernel)
+    uint32_t n_ord_rows;    // rows with >= 2 predecessors: they own a block of predecessor ordinals in the warp kernel's trace
 };
 
 struct AlnDesc {
@@ -34,7 +35,8 @@ struct AlnDesc {
     uint32_t Q;
     uint32_t W;           // padded row width (multiple of 4, >= Q + 1)
     uint32_t query_base;  // into queries
-    uint64_t trace_base;  // into the trace store (elements), V * W elements
+    uint64_t trace_base;  // into the trace store (elements), V * W elements (CTA kernel: one word per cell)
+    uint64_t ptrace_base; // into the trace store (32-bit words): V * 256 bit-plane words + n_ord_rows * 1024 ordinals (warp kernel)
     uint32_t out_base;    // into the pair output staging area, capacity V + Q + 2
     uint32_t out_cap;
 };
@@ -50,9 +52,10 @@ struct PackedBatch {
     std::vector<GraphDesc> graphs;
     std::vector<AlnDesc> alns;
     std::vector<uint8_t> node_sym;
-    std::vector<uint32_t> node_info, node_id, pred_off, pred_rank, pred_slot;
+    std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
     std::vector<uint8_t> queries;
     uint64_t trace_elems = 0;
+    uint64_t ptrace_words = 0;
     uint64_t out_elems = 0;
     uint64_t max_cells = 0;  // max over alignments of V * W
     uint64_t max_store_cells = 0;  // max over alignments of n_stored * W (warp kernel's compact row store)
@@ -66,11 +69,12 @@ struct PackedBatch {
         node_sym.clear();
         node_info.clear();
         node_id.clear();
+        ord_slot.clear();
         pred_off.clear();
         pred_rank.clear();
         pred_slot.clear();
         queries.clear();
-        trace_elems = out_elems = max_cells = total_cells = max_store_cells = 0;
+        trace_elems = ptrace_words = out_elems = max_cells = total_cells = max_store_cells = 0;
         max_in_degree = 0;
         max_W = 0;
     }
@@ -85,10 +89,12 @@ struct PackedBatch {
         gd.node_base = (uint32_t)node_sym.size();
         gd.predoff_base = (uint32_t)pred_off.size();
         gd.max_in_degree = 0;
+        gd.n_ord_rows = 0;
         for (uint32_t r = 0; r < V; ++r) {
             const uint32_t v = g.topo_order[r];
             node_sym.push_back(g.symbol[v]);
             node_id.push_back(v);
+            ord_slot.push_back(g.pred_off[v + 1] - g.pred_off[v] >= 2 ? gd.n_ord_rows++ : 0xFFFFFFFFu);
             uint32_t info = 0;
             bool has_end = false, have_sym = false, multi = false;
             uint8_t usym = 0;
@@ -114,13 +120,13 @@ struct PackedBatch {
             gd.max_in_degree = std::max(gd.max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
         }
         pred_off.push_back((uint32_t)pred_rank.size());
-        // rows read through the row store: every predecessor of a row that is not "single predecessor = previous row"
+        // rows read through the row store: every predecessor that is not the row just before its successor (that one is
+        // still in registers when the successor is computed)
         const uint32_t pr0 = pred_off[gd.predoff_base];
         for (uint32_t r = 0; r < V; ++r) {
             const uint32_t b = pred_off[gd.predoff_base + r], e2 = pred_off[gd.predoff_base + r + 1];
-            const bool fast = (e2 - b == 1) && pred_rank[b] == r - 1 && !(node_info[gd.node_base + r] & INFO_IS_END);
-            if (fast) continue;
-            for (uint32_t k = b; k < e2; ++k) node_info[gd.node_base + pred_rank[k]] |= INFO_STORE;
+            for (uint32_t k = b; k < e2; ++k)
+                if (pred_rank[k] != r - 1) node_info[gd.node_base + pred_rank[k]] |= INFO_STORE;
         }
         gd.n_stored = 0;
         for (uint32_t r = 0; r < V; ++r)
@@ -146,6 +152,8 @@ struct PackedBatch {
         const uint64_t V = graphs[graph].V;
         a.trace_base = trace_elems;
         trace_elems += V * a.W;
+        a.ptrace_base = ptrace_words;
+        ptrace_words += V * 256 + (uint64_t)graphs[graph].n_ord_rows * 1024;
         a.out_cap = (uint32_t)V + Q + 2;
         a.out_base = (uint32_t)out_elems;
         out_elems += a.out_cap;

@@ -1,17 +1,22 @@
-// dp_fill_warp_kernel — v2 of the M/I/D fill (included by align.cu after BatchDev / TraceFmt).
+// dp_fill_warp_kernel — the M/I/D fill for queries up to 1023 bases (included by align.cu after BatchDev).
 //
 // One WARP per alignment, no block barriers. Lane l owns the 32 contiguous query columns [32 l, 32 l + 32)
-// of every row (queries up to 1023 bases; longer ones take the CTA-per-alignment kernel). The previous row's
-// M and D for those columns live in REGISTERS, so a row whose only predecessor is the row just computed (the
-// common case in a POA graph laid out in topological order) touches no memory except its traceback words:
+// of every row. The previous row's M and D for those columns live in REGISTERS, so a row whose only
+// predecessor is the row just computed (the common case in a POA graph laid out in topological order)
+// touches no memory except its traceback bits:
 //   * diagonal / deletion terms straight from registers, the left neighbour's column via one shuffle;
-//   * symbol tests from per-lane 32-bit equality masks of the query (computed once per symbol and alignment);
+//   * symbol tests from per-lane 32-bit equality masks of the query (one pair per symbol and alignment);
 //   * the in-row insertion chain I[j] = o + j e + min_{k<j, openI(k)} (min(Mdiag, D)[k] - k e) as a sequential
 //     prefix-min over the lane's own columns plus ONE 5-step warp-shuffle prefix-min per row;
-//   * min-of-three / add-min recurrences through the DPX intrinsics (__vimin3_s32, __viaddmin_s32).
+//   * add-min recurrences through the DPX intrinsic __viaddmin_s32;
+//   * "infinite" is any value >= 2^28 (INF = 2^29): sums never overflow, so there is no clamping in the inner loops.
+// Traceback is stored as BIT PLANES: per (row, lane) eight 32-bit words
+//     [M<-diag, M<-D, M<-I, D<-open, D<-extend, I reachable, -, -]   (bit c = column 32 lane + c)
+// = 1 byte per cell, written with two 128-bit stores per lane and row; predecessor ordinals exist only for rows
+// with several predecessors (side store, 4 KB per such row). The meaning of the bits is the reference's
+// score-equality backtrace (gap_affine.rs:550-657), as in dp_fill_kernel.
 // Rows with several predecessors, or whose predecessor is not the previous row, read predecessor rows from a
 // per-warp row store in HBM; only rows that some later row needs from there are written to it (host flag).
-// Traceback words have the same meaning and layout as in dp_fill_kernel, so traceback_kernel serves both.
 #pragma once
 
 namespace poasta {
@@ -19,6 +24,9 @@ namespace poasta {
 constexpr int WARP_COLS = 32;      // columns per lane
 constexpr int WARP_MAX_W = 1024;   // 32 lanes x 32 columns
 constexpr int WARP_KERNEL_WARPS = 4;
+constexpr int WINF = 0x20000000;   // "infinite" score of the warp kernel
+constexpr int WFIN = 0x10000000;   // values below this are finite
+enum { PL_M_DIAG = 0, PL_M_DEL = 1, PL_M_INS = 2, PL_D_OPEN = 3, PL_D_EXT = 4, PL_I = 5, PL_WORDS = 8 };
 
 // per-lane equality masks of the query against one symbol:
 //   m bit c = (1 <= j <= Q && q[j-1] == s)   "column j matches s"      (j = 32 lane + c)
@@ -38,11 +46,9 @@ __device__ __forceinline__ SymMask make_mask(const uint8_t *q, int Q, int j0, in
     return r;
 }
 
-template <typename TraceT, bool WRITE_TRACE>
-__global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(BatchDev P) {
-    constexpr int OB = TraceFmt<TraceT>::ORD_BITS;
+template <bool WRITE_TRACE>
+__global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel(BatchDev P) {
     constexpr int C = WARP_COLS;
-    __shared__ uint32_t s_ords[WARP_KERNEL_WARPS][C][32];  // generic rows: packed predecessor ordinals per cell, [c][lane]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t worker = blockIdx.x * WARP_KERNEL_WARPS + wib;
     int *const slot = P.scratch + (uint64_t)worker * P.scratch_stride;
@@ -60,10 +66,11 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
         const uint8_t *q = P.queries + ad.query_base;
         const uint8_t *sym = P.node_sym + gd.node_base;
         const uint32_t *info = P.node_info + gd.node_base;
+        const uint32_t *ord_slot = P.ord_slot + gd.node_base;
         const uint32_t *poff = P.pred_off + gd.predoff_base;
-        TraceT *trace = (TraceT *)P.trace + ad.trace_base;
+        uint32_t *planes = (uint32_t *)P.trace + ad.ptrace_base;           // V * 32 lanes * PL_WORDS words
+        uint32_t *ord_store = planes + (uint64_t)V * 32 * PL_WORDS;         // n_ord_rows * 1024 words, [c][lane] per row
 
-        // equality masks for the four common symbols, others on demand
         const SymMask mA = make_mask(q, Q, j0, 'A'), mC = make_mask(q, Q, j0, 'C'), mG = make_mask(q, Q, j0, 'G'),
                       mT = make_mask(q, Q, j0, 'T');
         auto mask_of = [&](int s) -> SymMask {
@@ -73,17 +80,19 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
             if (s == 'T') return mT;
             return make_mask(q, Q, j0, s);
         };
-        uint32_t valid = 0, ltQ = 0;  // bit c: j <= Q, j < Q
+        uint32_t valid = 0, ltQ = 0, ge1 = 0;  // bit c: j <= Q, j < Q, j >= 1
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             if (j0 + c <= Q) valid |= 1u << c;
             if (j0 + c < Q) ltQ |= 1u << c;
+            if (j0 + c >= 1) ge1 |= 1u << c;
         }
         const bool lane_active = j0 < W;
+        const int Qj = Q - j0;  // (Q - j) = Qj - c
 
         int Mp[C], Dp[C];  // previous row (rank r-1), final values
 #pragma unroll
-        for (int c = 0; c < C; ++c) Mp[c] = INF, Dp[c] = INF;
+        for (int c = 0; c < C; ++c) Mp[c] = WINF, Dp[c] = WINF;
 
         for (int r = 0; r < V; ++r) {
             const uint32_t inf = info[r];
@@ -97,13 +106,13 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
             if ((inf & INFO_HAS_SUCC) && !is_end) openI_mask = (inf & INFO_ALWAYS_OPEN) ? ltQ : (ltQ & ~mask_of((int)(inf & 0xFF)).n);
             int Xr[C];                         // min(Mdiag, D) per column
             uint32_t diag_le = 0, d_open = 0;  // bit c: Mdiag <= D ; D equals the best "open" candidate
-            bool generic = true;
+            const uint32_t oslot = WRITE_TRACE ? ord_slot[r] : 0xFFFFFFFFu;
+            int prev_left = __shfl_up_sync(0xFFFFFFFFu, Mp[C - 1], 1);  // M[r-1][j0 - 1] (register copy of the previous row)
+            if (lane == 0) prev_left = WINF;
 
             if (npred == 1 && !is_end) {
                 // ---- single predecessor: registers (pred == r-1) or one reload from the row store ----
-                generic = false;
                 const int p = (int)P.pred_rank[pb];
-                int mleft;
                 if (p != r - 1) {
                     const int *Ms = slot + (uint64_t)(2 * P.pred_slot[pb]) * W;
                     if (lane_active) {
@@ -115,58 +124,61 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
                                 Mp[4 * k] = m4.x, Mp[4 * k + 1] = m4.y, Mp[4 * k + 2] = m4.z, Mp[4 * k + 3] = m4.w;
                                 Dp[4 * k] = d4.x, Dp[4 * k + 1] = d4.y, Dp[4 * k + 2] = d4.z, Dp[4 * k + 3] = d4.w;
                             } else {
-                                Mp[4 * k] = Mp[4 * k + 1] = Mp[4 * k + 2] = Mp[4 * k + 3] = INF;
-                                Dp[4 * k] = Dp[4 * k + 1] = Dp[4 * k + 2] = Dp[4 * k + 3] = INF;
+                                Mp[4 * k] = Mp[4 * k + 1] = Mp[4 * k + 2] = Mp[4 * k + 3] = WINF;
+                                Dp[4 * k] = Dp[4 * k + 1] = Dp[4 * k + 2] = Dp[4 * k + 3] = WINF;
                             }
                         }
                     }
                 }
-                mleft = __shfl_up_sync(0xFFFFFFFFu, Mp[C - 1], 1);
-                if (lane == 0) mleft = INF;
-                int prevM = mleft;  // M[p][j-1]
+                int prevM = prev_left;
+                if (p != r - 1) {  // reloaded row: fetch the left neighbour's last column again
+                    prevM = __shfl_up_sync(0xFFFFFFFFu, Mp[C - 1], 1);
+                    if (lane == 0) prevM = WINF;
+                }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int mpc = Mp[c];
-                    const int sub = (ms.m >> c) & 1 ? 0 : x;
-                    int mdiag = min(prevM + sub, INF);
-                    if (!((valid >> c) & 1) || (j0 + c) == 0) mdiag = INF;
-                    const int dopen = min(mpc + oe, INF);
-                    const int dext = min(Dp[c] + e, INF);
-                    int d = (openD_mask >> c) & 1 ? min(dopen, dext) : dext;
-                    if (!((valid >> c) & 1)) d = INF;
-                    if (d < INF && dopen == d) d_open |= 1u << c;
+                    const int mdiag = prevM + (((ms.m >> c) & 1) ? 0 : x);
+                    const int dopen = mpc + oe;
+                    const int dext = Dp[c] + e;
+                    const int d = ((openD_mask >> c) & 1) ? min(dopen, dext) : dext;
+                    if (dopen == d) d_open |= 1u << c;
                     if (mdiag <= d) diag_le |= 1u << c;
                     Xr[c] = min(mdiag, d);
                     Dp[c] = d;
                     prevM = mpc;
                 }
-            }
-            if (generic) {
+            } else {
                 // ---- start row, end row, several predecessors: every predecessor row comes from the row store ----
 #pragma unroll
                 for (int cc = 0; cc < C / 8; ++cc) {
                     int Xa[8], dom[8], dem[8];
                     uint32_t ords[8];  // mord | dopen_ord << 10 | dext_ord << 20
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) Xa[c] = INF, dom[c] = INF, dem[c] = INF, ords[c] = 0;
+                    for (int c = 0; c < 8; ++c) Xa[c] = WINF, dom[c] = WINF, dem[c] = WINF, ords[c] = 0;
                     const int jb = j0 + cc * 8;
                     if (jb < W) {
                         for (uint32_t k = pb; k < pe; ++k) {
                             const uint32_t ord = k - pb;
-                            const int *Ms = slot + (uint64_t)(2 * P.pred_slot[k]) * W;
-                            const int4 ma = *reinterpret_cast<const int4 *>(Ms + jb), mb = *reinterpret_cast<const int4 *>(Ms + jb + 4);
-                            const int4 da = *reinterpret_cast<const int4 *>(Ms + W + jb), db = *reinterpret_cast<const int4 *>(Ms + W + jb + 4);
-                            const int ml = jb > 0 ? Ms[jb - 1] : INF;
-                            const int mp[9] = {ml, ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-                            const int dp[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                            int mp[9], dp[8];
+                            if ((int)P.pred_rank[k] == r - 1) {  // the row just computed is still in registers
+                                mp[0] = cc == 0 ? prev_left : Mp[cc * 8 - (cc == 0 ? 0 : 1)];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) mp[c + 1] = Mp[cc * 8 + c], dp[c] = Dp[cc * 8 + c];
+                            } else {
+                                const int *Ms = slot + (uint64_t)(2 * P.pred_slot[k]) * W;
+                                const int4 ma = *reinterpret_cast<const int4 *>(Ms + jb), mb = *reinterpret_cast<const int4 *>(Ms + jb + 4);
+                                const int4 da = *reinterpret_cast<const int4 *>(Ms + W + jb), db = *reinterpret_cast<const int4 *>(Ms + W + jb + 4);
+                                mp[0] = jb > 0 ? Ms[jb - 1] : WINF;
+                                mp[1] = ma.x, mp[2] = ma.y, mp[3] = ma.z, mp[4] = ma.w, mp[5] = mb.x, mp[6] = mb.y, mp[7] = mb.z, mp[8] = mb.w;
+                                dp[0] = da.x, dp[1] = da.y, dp[2] = da.z, dp[3] = da.w, dp[4] = db.x, dp[5] = db.y, dp[6] = db.z, dp[7] = db.w;
+                            }
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const int cg = cc * 8 + c, j = jb + c;
-                                int cand;
-                                if (is_end) cand = mp[c + 1];
-                                else cand = (j >= 1 && j <= Q) ? min(mp[c] + ((ms.m >> cg) & 1 ? 0 : x), INF) : INF;
+                                const int cg = cc * 8 + c;
+                                const int cand = is_end ? mp[c + 1] : mp[c] + (((ms.m >> cg) & 1) ? 0 : x);
                                 if (cand < Xa[c]) Xa[c] = cand, ords[c] = (ords[c] & ~0x3FFu) | ord;
-                                const int dop = min(mp[c + 1] + oe, INF), dex = min(dp[c] + e, INF);
+                                const int dop = mp[c + 1] + oe, dex = dp[c] + e;
                                 if (dop < dom[c]) dom[c] = dop, ords[c] = (ords[c] & ~(0x3FFu << 10)) | (ord << 10);
                                 if (dex < dem[c]) dem[c] = dex, ords[c] = (ords[c] & ~(0x3FFu << 20)) | (ord << 20);
                             }
@@ -175,16 +187,17 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const int cg = cc * 8 + c, j = jb + c;
-                        const bool v = (valid >> cg) & 1;
-                        int d = v ? min((openD_mask >> cg) & 1 ? dom[c] : INF, dem[c]) : INF;
-                        int xd = v ? Xa[c] : INF;
+                        const int d = ((openD_mask >> cg) & 1) ? min(dom[c], dem[c]) : dem[c];
+                        int xd = Xa[c];
+                        if (!is_end && j == 0) xd = WINF;  // no diagonal into column 0
                         if (is_start && j == 0) xd = 0;
-                        bool is_open = d < INF && dom[c] == d;
-                        if (d < INF && !is_open && !((openD_mask >> cg) & 1) && npred > 1 && dom[c] < d) {
+                        bool is_open = dom[c] == d;
+                        if (WRITE_TRACE && d < WFIN && !is_open && !((openD_mask >> cg) & 1) && npred > 1 && dom[c] < d && j <= Q) {
                             // rare: a non-minimal "open" candidate equals D although opening is not allowed here
                             // (the reference's backtrace tests score equality only)
                             for (uint32_t k = pb; k < pe; ++k) {
-                                if (min(slot[(uint64_t)(2 * P.pred_slot[k]) * W + j] + oe, INF) == d) {
+                                const int mpj = (int)P.pred_rank[k] == r - 1 ? Mp[cg] : slot[(uint64_t)(2 * P.pred_slot[k]) * W + j];
+                                if (mpj + oe == d) {
                                     is_open = true;
                                     ords[c] = (ords[c] & ~(0x3FFu << 10)) | ((k - pb) << 10);
                                     break;
@@ -195,16 +208,16 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
                         if (xd <= d && !(is_start && j == 0)) diag_le |= 1u << cg;
                         Xr[cg] = min(xd, d);
                         Dp[cg] = d;
-                        s_ords[wib][cg][lane] = ords[c];
+                        if (WRITE_TRACE && oslot != 0xFFFFFFFFu && lane_active) ord_store[(uint64_t)oslot * 1024 + cg * 32 + lane] = ords[c];
                     }
                 }
             }
 
             // ---- insertion chain: prefix-min over the whole row ----
-            int run = INF;
+            int run = 2 * WINF - 1;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const int av = ((openI_mask >> c) & 1) && Xr[c] < INF ? Xr[c] + (Q - (j0 + c)) * e : INF;
+                const int av = ((openI_mask >> c) & 1) ? Xr[c] + (Qj - c) * e : 2 * WINF - 1;
                 run = min(run, av);
             }
             int incl = run;
@@ -214,76 +227,151 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) dp_fill_warp_kernel(Ba
                 if (lane >= d) incl = min(incl, o);
             }
             int pm = __shfl_up_sync(0xFFFFFFFFu, incl, 1);  // exclusive prefix-min over all columns left of mine
-            if (lane == 0) pm = INF;
+            if (lane == 0) pm = 2 * WINF - 1;
 
-            // ---- final M, traceback words, stores ----
-            TraceT *tp = trace + (uint64_t)r * W + j0;
-            int *Mrow = slot + (uint64_t)(2 * (inf >> INFO_SLOT_SHIFT)) * W + j0;
-            const bool store_row = inf & INFO_STORE;
+            // ---- final M and the traceback bit planes ----
+            uint32_t x_le_i = 0, i_le_x = 0, m_fin = 0, i_fin = 0, d_fin = 0, d_eq_m = 0;
+            const int ioff = oe - e;  // I[j] = pm + o - (Q - j) e
 #pragma unroll
-            for (int c8 = 0; c8 < C / 8; ++c8) {
-                uint32_t tw[8];
-#pragma unroll
-                for (int c = c8 * 8; c < c8 * 8 + 8; ++c) {
-                    const int j = j0 + c;
-                    const bool v = (valid >> c) & 1;
-                    const int iv = (v && j >= 1 && pm < INF) ? min(pm + oe - (Q - j) * e - e, INF) : INF;
-                    const int xr = Xr[c], dv = Dp[c];
-                    const int mv = min(xr, iv);
-                    // advance the running prefix with this column
-                    const int av = ((openI_mask >> c) & 1) && xr < INF ? xr + (Q - j) * e : INF;
-                    pm = min(pm, av);
-                    Mp[c] = mv;
-                    if (WRITE_TRACE) {
-                        uint32_t icode = iv < INF ? I_OPEN : I_NONE, mcode = M_NONE, dcode = D_NONE, mo = 0, dox = 0;
-                        uint32_t ords = 0;
-                        if (generic) ords = s_ords[wib][c][lane];
-                        if (dv < INF) {
-                            if ((d_open >> c) & 1) dcode = D_OPEN, dox = (ords >> 10) & 0x3FF;
-                            else dcode = D_EXT, dox = (ords >> 20) & 0x3FF;
-                        }
-                        if (mv < INF) {
-                            if (xr == mv) {
-                                if (((diag_le >> c) & 1) && j >= 1 && npred > 0) mcode = M_DIAG, mo = ords & 0x3FF;
-                                else if (dv == mv) mcode = M_DEL;
-                                else if (iv == mv) mcode = M_INS;
-                            } else {
-                                mcode = M_INS;
-                            }
-                        }
-                        tw[c - c8 * 8] = icode | (mcode << 2) | (dcode << 4) | (mo << 6) | (dox << (6 + OB));
-                    }
+            for (int c = 0; c < C; ++c) {
+                const int kje = (Qj - c) * e;
+                const int iv = pm + ioff - kje;
+                const int xr = Xr[c], dv = Dp[c];
+                const int mv = min(xr, iv);
+                const int av = ((openI_mask >> c) & 1) ? xr + kje : 2 * WINF - 1;
+                pm = min(pm, av);
+                Mp[c] = mv;
+                if (WRITE_TRACE) {
+                    if (xr <= iv) x_le_i |= 1u << c;
+                    if (iv <= xr) i_le_x |= 1u << c;
+                    if (mv < WFIN) m_fin |= 1u << c;
+                    if (iv < WFIN) i_fin |= 1u << c;
+                    if (dv < WFIN) d_fin |= 1u << c;
+                    if (dv == mv) d_eq_m |= 1u << c;
                 }
-                if (lane_active && j0 + c8 * 8 < W) {
-                    if (WRITE_TRACE) {
-                        if constexpr (sizeof(TraceT) == 2) {
-                            *reinterpret_cast<uint4 *>(tp + c8 * 8) = make_uint4(tw[0] | (tw[1] << 16), tw[2] | (tw[3] << 16),
-                                                                                 tw[4] | (tw[5] << 16), tw[6] | (tw[7] << 16));
-                        } else {
-                            *reinterpret_cast<uint4 *>(tp + c8 * 8) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
-                            *reinterpret_cast<uint4 *>(tp + c8 * 8 + 4) = make_uint4(tw[4], tw[5], tw[6], tw[7]);
-                        }
-                    }
-                    if (store_row) {
-                        const int b = c8 * 8;
+            }
+            if (WRITE_TRACE && lane_active) {
+                // gap_affine.rs:577-613: predecessors first (offset > 0), then close-deletion, then close-insertion
+                const uint32_t m_diag = m_fin & x_le_i & diag_le & ge1 & (npred > 0 ? ~0u : 0u);
+                const uint32_t m_del = m_fin & ~m_diag & d_eq_m;
+                const uint32_t m_ins = m_fin & ~m_diag & ~m_del & i_le_x;
+                const uint32_t pd_open = d_fin & d_open, pd_ext = d_fin & ~d_open;
+                uint4 *tp = reinterpret_cast<uint4 *>(planes + ((uint64_t)r * 32 + lane) * PL_WORDS);
+                tp[0] = make_uint4(m_diag & valid, m_del & valid, m_ins & valid, pd_open & valid);
+                tp[1] = make_uint4(pd_ext & valid, i_fin & valid & ge1, 0u, 0u);
+            }
+            if ((inf & INFO_STORE) && lane_active) {
+                int *Mrow = slot + (uint64_t)(2 * (inf >> INFO_SLOT_SHIFT)) * W + j0;
+#pragma unroll
+                for (int b = 0; b < C; b += 4) {
+                    if (j0 + b < W) {
                         *reinterpret_cast<int4 *>(Mrow + b) = make_int4(Mp[b], Mp[b + 1], Mp[b + 2], Mp[b + 3]);
-                        *reinterpret_cast<int4 *>(Mrow + b + 4) = make_int4(Mp[b + 4], Mp[b + 5], Mp[b + 6], Mp[b + 7]);
                         *reinterpret_cast<int4 *>(Mrow + W + b) = make_int4(Dp[b], Dp[b + 1], Dp[b + 2], Dp[b + 3]);
-                        *reinterpret_cast<int4 *>(Mrow + W + b + 4) = make_int4(Dp[b + 4], Dp[b + 5], Dp[b + 6], Dp[b + 7]);
                     }
                 }
             }
-            if (store_row) __syncwarp();  // row-store writes of this warp are read by other lanes of the same warp later
+            if (inf & INFO_STORE) __syncwarp();  // row-store writes of this warp are read by other lanes of the same warp later
             if (is_end && j0 <= Q && Q < j0 + C) {
-                int sc = INF;
+                int sc = WINF;
 #pragma unroll
                 for (int c = 0; c < C; ++c)
                     if (j0 + c == Q) sc = Mp[c];
-                P.scores[a] = (uint32_t)sc;
+                P.scores[a] = sc < WFIN ? (uint32_t)sc : (uint32_t)INF;
             }
         }
         __syncwarp();
     }
+}
+
+// gap_affine.rs:804-915 on the bit planes written by dp_fill_warp_kernel. One thread per alignment.
+__global__ void traceback_planes_kernel(BatchDev P) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.n_alns) return;
+    const AlnDesc ad = P.alns[a];
+    const GraphDesc gd = P.graphs[ad.graph];
+    const int Q = (int)ad.Q, V = (int)gd.V;
+    const uint32_t *node_id = P.node_id + gd.node_base;
+    const uint32_t *ord_slot = P.ord_slot + gd.node_base;
+    const uint32_t *poff = P.pred_off + gd.predoff_base;
+    const uint32_t *planes = (const uint32_t *)P.trace + ad.ptrace_base;
+    const uint32_t *ord_store = planes + (uint64_t)V * 32 * PL_WORDS;
+    uint32_t *out_r = P.out_r + ad.out_base, *out_q = P.out_q + ad.out_base;
+    uint32_t pos = ad.out_cap;  // fill from the back
+    int32_t status = 0;
+    const uint32_t score = P.scores[a];
+    auto bit = [&](int r, int o, int plane) -> bool {
+        return (planes[((uint64_t)r * 32 + (o >> 5)) * PL_WORDS + plane] >> (o & 31)) & 1;
+    };
+    auto ord_of = [&](int r, int o, int shift) -> uint32_t {
+        const uint32_t s = ord_slot[r];
+        if (s == 0xFFFFFFFFu) return 0;
+        return (ord_store[(uint64_t)s * 1024 + (o & 31) * 32 + (o >> 5)] >> shift) & 0x3FF;
+    };
+    if (score >= (uint32_t)INF) {
+        status = POASTA_ERR_NO_ALIGNMENT;
+    } else if (Q == 1) {  // gap_affine.rs:812-824
+        --pos;
+        out_r[pos] = node_id[V - 1];
+        out_q[pos] = 0;
+    } else if (Q > 1) {
+        auto step = [&](int r, int o, int s, int &nr, int &no, int &ns) -> bool {
+            if (s == 0) {
+                if (bit(r, o, PL_M_DIAG)) {
+                    nr = (int)P.pred_rank[poff[r] + ord_of(r, o, 0)];
+                    no = (r == V - 1) ? o : o - 1;
+                    ns = 0;
+                    return true;
+                }
+                if (bit(r, o, PL_M_DEL)) {
+                    nr = r, no = o, ns = 1;
+                    return true;
+                }
+                if (bit(r, o, PL_M_INS)) {
+                    nr = r, no = o, ns = 2;
+                    return true;
+                }
+                return false;
+            } else if (s == 1) {
+                if (bit(r, o, PL_D_OPEN)) {
+                    nr = (int)P.pred_rank[poff[r] + ord_of(r, o, 10)];
+                    no = o, ns = 0;
+                    return true;
+                }
+                if (bit(r, o, PL_D_EXT)) {
+                    nr = (int)P.pred_rank[poff[r] + ord_of(r, o, 20)];
+                    no = o, ns = 1;
+                    return true;
+                }
+                return false;
+            } else {
+                if (!bit(r, o, PL_I)) return false;
+                nr = r, no = o - 1, ns = 0;  // both open and extend resume in Match state (gap_affine.rs:639-650)
+                return true;
+            }
+        };
+        int cr = V - 1, co = Q, cs = 0, br = 0, bo = 0, bs = 0;
+        if (step(cr, co, cs, br, bo, bs)) {
+            cr = br, co = bo, cs = bs;
+            while (step(cr, co, cs, br, bo, bs)) {
+                if (cs == 0 && bs != 0) {
+                    cr = br, co = bo, cs = bs;
+                    continue;
+                }
+                if (pos == 0) {
+                    status = POASTA_ERR_UNSUPPORTED;
+                    break;
+                }
+                --pos;
+                if (cs == 0) out_r[pos] = node_id[cr], out_q[pos] = (uint32_t)(co - 1);
+                else if (cs == 2) out_r[pos] = POASTA_NONE, out_q[pos] = (uint32_t)(co - 1);
+                else out_r[pos] = node_id[cr], out_q[pos] = POASTA_NONE;
+                if (br == 0) break;  // predecessor is the start node (rank 0)
+                cr = br, co = bo, cs = bs;
+            }
+        }
+    }
+    P.n_pairs[a] = ad.out_cap - pos;
+    P.status[a] = status;
 }
 
 }  // namespace poasta
