@@ -5,8 +5,8 @@
 
 One "step" = one progressive-MSA pass of the hot path over one batch of F families (19 alignment rounds,
 each round one device batch), called through the public C-ABI entry `poasta_msa_batch` with HOST buffers.
-Step k aligns families [k*F, (k+1)*F) with F = 10,000 by default, i.e. every step is one full instance of
-BASELINE.json's config 2 (different families each step, same shape); warm-up steps use further families.
+Step k aligns families [k*F, (k+1)*F) with F = 5,000 by default: the default 2 steps are BASELINE.json's config 2
+(10,000 families); warm-up steps use further families of the same shape.
   value   GCUPS over the device kernels only (CUDA events on the launching stream around the DP fill /
           traceback and the order-exact search launches; inputs of each launch resident in HBM);
   e2e     GCUPS of the whole call: FASTA text in host memory -> final graphs, including flattening,
@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "10000")), help="families per step per GPU")
+    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "5000")), help="families per step per GPU")
     ap.add_argument("--tiebreak", default=os.environ.get("BENCH_TIEBREAK", "exact"), choices=["exact", "dp"])
     ap.add_argument("--seqs", type=int, default=20)
     ap.add_argument("--length", type=int, default=1000)

@@ -37,6 +37,14 @@
 #define RP_HD inline
 #endif
 
+// non-binding L1 prefetch hints. Measured on B200 (profiles/README.md): prefetch.global.L1 at the points below made the
+// kernel 20 % SLOWER (3.70 s vs 3.09 s per 20,000 alignments), so the hints are compiled out unless RP_USE_PREFETCH is set.
+#if defined(__CUDA_ARCH__) && defined(RP_USE_PREFETCH)
+#define RP_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define RP_PREFETCH(p) ((void)0)
+#endif
+
 // optional cycle accounting of the device build (-DRP_PROFILE): where a worker's time goes
 #if defined(RP_PROFILE) && defined(__CUDA_ARCH__)
 #define RP_T0 const long long _t0 = clock64()
@@ -130,6 +138,13 @@ RP_HD int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_e
     constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
     bool wrapped = false;
     auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
+    // issue the loads every bubble will need (reached bounds and the exit's Match row around the target offset) before
+    // evaluating any of them, so their DRAM latencies overlap instead of adding up
+    for (uint32_t k = bub_begin; k < bub_end; ++k) {
+        const uint32_t exit = c.bub[4 * k];
+        RP_PREFETCH(c.rb + 2 * (size_t)exit);
+        RP_PREFETCH(c.m_plane + (size_t)exit * c.W + off + c.bub[4 * k + 1]);
+    }
     for (uint32_t k = bub_begin; k < bub_end; ++k) {
         const uint32_t exit = c.bub[4 * k], min_d = c.bub[4 * k + 1], max_d = c.bub[4 * k + 2], mde = c.bub[4 * k + 3];
         const uint32_t lo = c.rb[2 * exit], hi1 = c.rb[2 * exit + 1];
@@ -487,6 +502,7 @@ struct Search {
                 err = RP_EMPTY_QUEUE;
                 break;
             }
+            RP_PREFETCH(g.nodes + it.node);
             if (it.score > get(it.node, it.offset, st)) continue;
             if (is_end(it.node, it.offset, st)) {
                 ++res.num_visited;
@@ -542,7 +558,10 @@ struct Search {
                                 kind = 2, cn = child;
                                 break;
                             }
+                            RP_PREFETCH(cell(child, po + 1, ST_M));  // needed right after the symbol test; overlaps the record load
                             ca = node_a(child);
+                            RP_PREFETCH(g.bub + 4 * (size_t)ca.bub_off);
+                            RP_PREFETCH(g.succ + ca.succ_off);
                             if ((ca.symflags & 0xFF) == q[po]) {
                                 if (relax(child, po + 1, ST_M, score)) {
                                     kind = 3, cn = child, co = po + 1;
