@@ -797,7 +797,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
 
     CK(cudaEventRecord(c.ev0, s));
     {
-        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 32;
+        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 14;
         const dim3 grid((unsigned)(workers / warps_per_cta)), block(warps_per_cta * 32);
         if (cell16) {
             if (minb >= 32) replay_kernel<uint16_t, 32><<<grid, block, 0, s>>>(B);
