@@ -642,6 +642,8 @@ struct Problem {
     const uint8_t *query;
     uint32_t qlen;
     const SearchIndex *sidx;  // optional prebuilt index for the order-exact search (built on demand when null)
+    const PackedGraph *packed = nullptr;               // optional prebuilt rank-ordered layout (DP kernels)
+    const std::vector<replay::NodeRec> *recs = nullptr;  // optional prebuilt node records (search kernel)
 };
 
 // DP path: aligns all problems; calls sink(i, score, status, rpos*, qpos*, n_pairs) per problem in order.
@@ -673,7 +675,7 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
             const uint64_t add = V * ((p.qlen + 4) & ~3ull) * 4;
             if (!pb.alns.empty() && (pb.trace_elems * 2 + add > budget || pb.alns.size() >= (1u << 20))) break;
             if (p.graph_key != last_key || pb.graphs.empty()) {
-                last_gid = pb.add_graph(*p.graph, rank_scratch);
+                last_gid = p.packed ? pb.add_packed(*p.packed) : pb.add_graph(*p.graph, rank_scratch);
                 last_key = p.graph_key;
             }
             pb.add_alignment(last_gid, p.query, p.qlen);
@@ -888,7 +890,7 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
                     tmp.build(*p.graph, prm.heuristic == 2);
                     si = &tmp;
                 }
-                last_gid = pr.add_graph(*p.graph, *si);
+                last_gid = pr.add_graph(*p.graph, *si, p.recs);
                 last_key = p.graph_key;
             }
             pr.add_alignment(last_gid, p.query, p.qlen);
@@ -971,7 +973,7 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
         if (gi >= n_graphs) return POASTA_ERR_INVALID_ARG;
-        probs[i] = {&graphs[gi], gi, queries[i], qlens[i], nullptr};
+        probs[i] = {&graphs[gi], gi, queries[i], qlens[i], nullptr, nullptr, nullptr};
     }
     return align_problems(device, probs, *params,
                           [&](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
@@ -1042,10 +1044,13 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
     std::vector<Problem> probs;
     std::vector<uint32_t> fam_of_prob;
     std::vector<poasta_graph_view> views(n_families);
+    static const bool timing = getenv("POASTA_TIMING") != nullptr;  // per-phase host timers of one lane (stderr)
+    double t_index = 0, t_align = 0, t_insert = 0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     struct Pending {
         uint32_t score;
         int32_t status;
-        std::vector<AlignedPair> aln;
+        std::vector<uint32_t> r, q;
     };
     std::vector<Pending> pending;
     for (size_t round = 0; round < max_round; ++round) {
@@ -1067,28 +1072,34 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
         }
         if (to_align.empty()) continue;
         const bool need_index = params->tiebreak == 0;
+        const double t0 = now();
+        const bool need_pack = params->mode == 0;  // the DP kernels run in both tiebreak modes of global alignment
         parallel_for(to_align.size(), [&](size_t k) {
             poasta_graph *h = graphs[to_align[k]];
             views[to_align[k]] = h->flat_view();
             if (need_index) h->search_index(params->heuristic == 2);
+            if (need_pack) h->packed_graph();
         });
         for (uint32_t f : to_align) {
             const FastaRecord &rec = recs[f][round];
             probs.push_back({&views[f], f, (const uint8_t *)rec.seq.data(), (uint32_t)rec.seq.size(),
-                             need_index ? &graphs[f]->sidx : nullptr});
+                             need_index ? &graphs[f]->sidx : nullptr, need_pack ? &graphs[f]->packed : nullptr,
+                             need_index ? &graphs[f]->node_recs : nullptr});
             fam_of_prob.push_back(f);
             cells += (uint64_t)graphs[f]->g.node_count() * rec.seq.size();
         }
         pending.assign(probs.size(), Pending{});
+        const double t1 = now();
         int rc = align_problems(device, probs, *params,
                                 [&](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
                                     Pending &p = pending[i];
                                     p.score = score;
                                     p.status = status;
-                                    p.aln.resize(np);
-                                    for (uint32_t t = 0; t < np; ++t) p.aln[t] = {r[t], q[t]};
+                                    p.r.assign(r, r + np);
+                                    p.q.assign(q, q + np);
                                 });
         if (rc) return rc;
+        const double t2 = now();
         parallel_for(probs.size(), [&](size_t i) {
             const uint32_t f = fam_of_prob[i];
             const FastaRecord &rec = recs[f][round];
@@ -1097,13 +1108,20 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
                 return;
             }
             graphs[f]->flat_valid = false;
+            std::vector<AlignedPair> aln(pending[i].r.size());
+            for (size_t t = 0; t < aln.size(); ++t) aln[t] = {pending[i].r[t], pending[i].q[t]};
             GraphError ge = graphs[f]->g.add_alignment_with_weights(rec.name, (const uint8_t *)rec.seq.data(), rec.seq.size(), true,
-                                                                    pending[i].aln.data(), pending[i].aln.size());
+                                                                    aln.data(), aln.size());
             if (ge != GraphError::Ok) err = ge == GraphError::InvalidAlignment ? POASTA_ERR_INVALID_ALIGNMENT : POASTA_ERR_GRAPH_CYCLE;
             if (scores_out) scores_out[score_base[f] + round] = pending[i].score;
         });
         if (err) return err;
+        const double t3 = now();
+        t_index += t1 - t0, t_align += t2 - t1, t_insert += t3 - t2;
     }
+    if (timing)
+        fprintf(stderr, "poasta_b200 lane %d: flatten+index %.2f s, align (pack + copies + kernels) %.2f s of which kernels %.2f s, insert %.2f s\n",
+                tl_lane, t_index, t_align, (tl_kernel_ms + tl_search_ms) / 1e3, t_insert);
     *cells_out = cells;
     return 0;
 }

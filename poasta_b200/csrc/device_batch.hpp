@@ -48,6 +48,63 @@ constexpr uint32_t INFO_IS_START = 1u << 11;
 constexpr uint32_t INFO_STORE = 1u << 12;  // some later row reads this row from the row store (warp kernel)
 constexpr uint32_t INFO_SLOT_SHIFT = 13;   // bits 13.. : index of the row inside the compact row store
 
+// One graph in the kernels' rank-ordered layout (see the header comment); pred_off is relative to this graph's pred_rank.
+struct PackedGraph {
+    uint32_t V = 0, max_in_degree = 0, n_stored = 0, n_ord_rows = 0;
+    std::vector<uint8_t> node_sym;
+    std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
+
+    void build(const poasta_graph_view &g, std::vector<uint32_t> &rank_scratch) {
+        V = g.n_nodes;
+        rank_scratch.resize(V);
+        for (uint32_t r = 0; r < V; ++r) rank_scratch[g.topo_order[r]] = r;
+        node_sym.clear(), node_info.clear(), node_id.clear(), ord_slot.clear(), pred_off.clear(), pred_rank.clear(), pred_slot.clear();
+        max_in_degree = n_stored = n_ord_rows = 0;
+        for (uint32_t r = 0; r < V; ++r) {
+            const uint32_t v = g.topo_order[r];
+            node_sym.push_back(g.symbol[v]);
+            node_id.push_back(v);
+            ord_slot.push_back(g.pred_off[v + 1] - g.pred_off[v] >= 2 ? n_ord_rows++ : 0xFFFFFFFFu);
+            uint32_t info = 0;
+            bool has_end = false, have_sym = false, multi = false;
+            uint8_t usym = 0;
+            for (uint32_t k = g.succ_off[v]; k < g.succ_off[v + 1]; ++k) {
+                const uint32_t s = g.succ[k];
+                info |= INFO_HAS_SUCC;
+                if (s == g.end_node) {
+                    has_end = true;
+                } else if (!have_sym) {
+                    usym = g.symbol[s];
+                    have_sym = true;
+                } else if (g.symbol[s] != usym) {
+                    multi = true;
+                }
+            }
+            if (has_end || multi) info |= INFO_ALWAYS_OPEN;
+            info |= usym;
+            if (v == g.end_node) info |= INFO_IS_END;
+            if (v == g.start_node) info |= INFO_IS_START;
+            node_info.push_back(info);
+            pred_off.push_back((uint32_t)pred_rank.size());
+            for (uint32_t k = g.pred_off[v]; k < g.pred_off[v + 1]; ++k) pred_rank.push_back(rank_scratch[g.pred[k]]);
+            max_in_degree = std::max(max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
+        }
+        pred_off.push_back((uint32_t)pred_rank.size());
+        // rows read through the row store: every predecessor that is not the row just before its successor (that one is
+        // still in registers when the successor is computed)
+        for (uint32_t r = 0; r < V; ++r)
+            for (uint32_t k = pred_off[r]; k < pred_off[r + 1]; ++k)
+                if (pred_rank[k] != r - 1) node_info[pred_rank[k]] |= INFO_STORE;
+        for (uint32_t r = 0; r < V; ++r)
+            if (node_info[r] & INFO_STORE) node_info[r] |= (n_stored++) << INFO_SLOT_SHIFT;
+        pred_slot.resize(pred_rank.size());
+        for (uint32_t k = 0; k < pred_rank.size(); ++k) {
+            const uint32_t pi = node_info[pred_rank[k]];
+            pred_slot[k] = (pi & INFO_STORE) ? (pi >> INFO_SLOT_SHIFT) : 0xFFFFFFFFu;
+        }
+    }
+};
+
 struct PackedBatch {
     std::vector<GraphDesc> graphs;
     std::vector<AlnDesc> alns;
@@ -81,61 +138,30 @@ struct PackedBatch {
 
     // Appends one graph; returns its id. `rank_scratch` avoids reallocation across calls.
     uint32_t add_graph(const poasta_graph_view &g, std::vector<uint32_t> &rank_scratch) {
-        const uint32_t V = g.n_nodes;
-        rank_scratch.resize(V);
-        for (uint32_t r = 0; r < V; ++r) rank_scratch[g.topo_order[r]] = r;
+        PackedGraph pg;
+        pg.build(g, rank_scratch);
+        return add_packed(pg);
+    }
+
+    // Appends a graph packed earlier (pack once per graph on a host worker thread, concatenate here).
+    uint32_t add_packed(const PackedGraph &pg) {
         GraphDesc gd;
-        gd.V = V;
+        gd.V = pg.V;
         gd.node_base = (uint32_t)node_sym.size();
         gd.predoff_base = (uint32_t)pred_off.size();
-        gd.max_in_degree = 0;
-        gd.n_ord_rows = 0;
-        for (uint32_t r = 0; r < V; ++r) {
-            const uint32_t v = g.topo_order[r];
-            node_sym.push_back(g.symbol[v]);
-            node_id.push_back(v);
-            ord_slot.push_back(g.pred_off[v + 1] - g.pred_off[v] >= 2 ? gd.n_ord_rows++ : 0xFFFFFFFFu);
-            uint32_t info = 0;
-            bool has_end = false, have_sym = false, multi = false;
-            uint8_t usym = 0;
-            for (uint32_t k = g.succ_off[v]; k < g.succ_off[v + 1]; ++k) {
-                const uint32_t s = g.succ[k];
-                info |= INFO_HAS_SUCC;
-                if (s == g.end_node) {
-                    has_end = true;
-                } else if (!have_sym) {
-                    usym = g.symbol[s];
-                    have_sym = true;
-                } else if (g.symbol[s] != usym) {
-                    multi = true;
-                }
-            }
-            if (has_end || multi) info |= INFO_ALWAYS_OPEN;
-            info |= usym;
-            if (v == g.end_node) info |= INFO_IS_END;
-            if (v == g.start_node) info |= INFO_IS_START;
-            node_info.push_back(info);
-            pred_off.push_back((uint32_t)pred_rank.size());
-            for (uint32_t k = g.pred_off[v]; k < g.pred_off[v + 1]; ++k) pred_rank.push_back(rank_scratch[g.pred[k]]);
-            gd.max_in_degree = std::max(gd.max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
-        }
-        pred_off.push_back((uint32_t)pred_rank.size());
-        // rows read through the row store: every predecessor that is not the row just before its successor (that one is
-        // still in registers when the successor is computed)
-        const uint32_t pr0 = pred_off[gd.predoff_base];
-        for (uint32_t r = 0; r < V; ++r) {
-            const uint32_t b = pred_off[gd.predoff_base + r], e2 = pred_off[gd.predoff_base + r + 1];
-            for (uint32_t k = b; k < e2; ++k)
-                if (pred_rank[k] != r - 1) node_info[gd.node_base + pred_rank[k]] |= INFO_STORE;
-        }
-        gd.n_stored = 0;
-        for (uint32_t r = 0; r < V; ++r)
-            if (node_info[gd.node_base + r] & INFO_STORE) node_info[gd.node_base + r] |= (gd.n_stored++) << INFO_SLOT_SHIFT;
-        pred_slot.resize(pred_rank.size());
-        for (uint32_t k = pr0; k < pred_rank.size(); ++k) {
-            const uint32_t pi = node_info[gd.node_base + pred_rank[k]];
-            pred_slot[k] = (pi & INFO_STORE) ? (pi >> INFO_SLOT_SHIFT) : 0xFFFFFFFFu;
-        }
+        gd.max_in_degree = pg.max_in_degree;
+        gd.n_stored = pg.n_stored;
+        gd.n_ord_rows = pg.n_ord_rows;
+        node_sym.insert(node_sym.end(), pg.node_sym.begin(), pg.node_sym.end());
+        node_info.insert(node_info.end(), pg.node_info.begin(), pg.node_info.end());
+        node_id.insert(node_id.end(), pg.node_id.begin(), pg.node_id.end());
+        ord_slot.insert(ord_slot.end(), pg.ord_slot.begin(), pg.ord_slot.end());
+        const uint32_t base = (uint32_t)pred_rank.size();
+        const size_t o0 = pred_off.size();
+        pred_off.insert(pred_off.end(), pg.pred_off.begin(), pg.pred_off.end());
+        for (size_t i = o0; i < pred_off.size(); ++i) pred_off[i] += base;
+        pred_rank.insert(pred_rank.end(), pg.pred_rank.begin(), pg.pred_rank.end());
+        pred_slot.insert(pred_slot.end(), pg.pred_slot.begin(), pg.pred_slot.end());
         max_in_degree = std::max(max_in_degree, gd.max_in_degree);
         graphs.push_back(gd);
         return (uint32_t)graphs.size() - 1;

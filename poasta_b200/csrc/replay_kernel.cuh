@@ -129,7 +129,7 @@ struct PackedReplay {
         max_V = max_Q = 0;
     }
 
-    uint32_t add_graph(const poasta_graph_view &v, const SearchIndex &si) {
+    uint32_t add_graph(const poasta_graph_view &v, const SearchIndex &si, const std::vector<replay::NodeRec> *recs = nullptr) {
         RGraphDesc gd;
         const uint32_t V = v.n_nodes;
         gd.V = V, gd.start = v.start_node, gd.end = v.end_node;
@@ -139,7 +139,8 @@ struct PackedReplay {
         gd.bub_base = (uint32_t)(bub.size() / 4);
         gd.path_base = (uint32_t)path_rem.size();
         gd.pathoff_base = (uint32_t)path_off.size();
-        si.node_records(v, nodes);
+        if (recs) nodes.insert(nodes.end(), recs->begin(), recs->end());
+        else si.node_records(v, nodes);
         succ.insert(succ.end(), v.succ, v.succ + v.succ_off[V]);
         pred.insert(pred.end(), v.pred, v.pred + v.pred_off[V]);
         bub.insert(bub.end(), si.bub.begin(), si.bub.end());
