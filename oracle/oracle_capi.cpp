@@ -303,16 +303,16 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     si.node_records(*view, recs);
     std::vector<uint32_t> path_off_zero;
     if (si.path_off.empty()) path_off_zero.assign(view->n_nodes + 1, 0);
-    rp::Graph g{view->n_nodes, view->start_node, view->end_node, recs.data(), view->succ, view->pred, si.bub.data(),
+    rp::Graph g{view->n_nodes, view->start_node, view->end_node, recs.data(), view->succ, view->pred, reinterpret_cast<const rp::BubQ *>(si.bub.data()),
                 si.path_off.empty() ? path_off_zero.data() : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
     ScratchDims d(view->n_nodes, qlen, x, o, e);
     std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), qwin(rp::QWIN * 3, 0), rb((size_t)view->n_nodes * 2, 0),
         dfa((size_t)(view->n_nodes + 2) * 6, 0);
     const uint32_t max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
     const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
-    std::vector<uint8_t> planes((size_t)3 * plane_elems * (cell16 ? 2 : 4));
-    if (cell16) std::fill((uint16_t *)planes.data(), (uint16_t *)planes.data() + 3 * plane_elems, (uint16_t)0x7FFF);
-    else std::fill((uint32_t *)planes.data(), (uint32_t *)planes.data() + 3 * plane_elems, 0x7FFFFFFFu);
+    std::vector<uint8_t> planes((size_t)rp::CELL_SLOTS * plane_elems * (cell16 ? 2 : 4));
+    if (cell16) std::fill((uint16_t *)planes.data(), (uint16_t *)planes.data() + rp::CELL_SLOTS * plane_elems, (uint16_t)0x7FFF);
+    else std::fill((uint32_t *)planes.data(), (uint32_t *)planes.data() + rp::CELL_SLOTS * plane_elems, 0x7FFFFFFFu);
     std::vector<Item> items(max_items);
     std::vector<uint32_t> free_slots(max_items);
     Scratch s{planes.data(), qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), plane_elems, d.W,
@@ -339,6 +339,13 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     }
     if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = used_blocks, stats[4] = used_items;
     return r.status;
+}
+
+// event counters of the host build of the search core (tools/search_stats.py); reading resets them
+int replay_host_counters(uint64_t *out, int cap) {
+    namespace rp = poasta::replay;
+    for (int i = 0; i < rp::C_N && i < cap; ++i) out[i] = rp::rp_counters[i], rp::rp_counters[i] = 0;
+    return rp::C_N;
 }
 
 void oracle_free(void *p) { free(p); }

@@ -721,7 +721,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
     const bool cell16 = worst < 0x7F00u;  // the top bit of a cell is the reached mark
-    const uint64_t plane_bytes = up(3 * cells_per_aln * (cell16 ? 2 : 4));
+    const uint64_t plane_bytes = up(replay::CELL_SLOTS * cells_per_aln * (cell16 ? 2 : 4));
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
     uint64_t max_items = full_arenas ? 262144 + cells_per_aln / 2 : 32768 + cells_per_aln / 32;

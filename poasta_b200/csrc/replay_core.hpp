@@ -54,6 +54,18 @@
 #define RP_ACC(x)
 #endif
 
+// optional event counters of the HOST build (-DRP_COUNT, tools/search_stats.py): what the state machine does per alignment
+#if defined(RP_COUNT) && !defined(__CUDA_ARCH__)
+namespace poasta { namespace replay {
+enum { C_POP_M, C_POP_D, C_POP_I, C_POP_STALE, C_DFA_STEP, C_DFA_MATCH, C_DFA_MISMATCH, C_DFA_RELAX_FAIL, C_PRUNE_CALL, C_PRUNE_BUB,
+       C_PRUNE_NOREACH, C_PRUNE_PROBE, C_PRUNE_SCORE, C_PUSH, C_RELAX, C_RELAX_OK, C_WINDOW_MOVE, C_POP_SCAN, C_N };
+inline uint64_t rp_counters[C_N];
+} }
+#define RP_CNT(x) (++::poasta::replay::rp_counters[::poasta::replay::x])
+#else
+#define RP_CNT(x) ((void)0)
+#endif
+
 namespace poasta {
 namespace replay {
 
@@ -61,6 +73,14 @@ constexpr uint32_t UNV = 0xFFFFFFFFu;  // Score::Unvisited
 enum : uint32_t { ST_M = 0, ST_D = 1, ST_I = 2 };
 enum : int { RP_OK = 0, RP_EMPTY_QUEUE = 1, RP_NO_BACKTRACE = 2, RP_SCORE_WRAP = 3, RP_OUT_OF_BLOCKS = 4, RP_OUT_OF_ITEMS = 5,
              RP_PRIORITY_RANGE = 6, RP_OUT_OF_PAIRS = 7 };
+// Visited-table layout: one record {Match, Deletion, Insertion, pad} per (node, offset). A popped state and the states it
+// relaxes mostly share (node, offset) or sit at the neighbouring offset, so they share a 32-byte sector, where three
+// separate planes cost one miss each. -DRP_PLANAR keeps the three-plane layout for A/B measurements.
+#if defined(RP_PLANAR)
+constexpr uint32_t CELL_SLOTS = 3, CELL_STRIDE = 1;
+#else
+constexpr uint32_t CELL_SLOTS = 4, CELL_STRIDE = 4;
+#endif
 constexpr uint32_t QWIN = 64;  // priorities whose stack heads are kept in the fast window
 
 struct alignas(16) NodeA {
@@ -68,11 +88,15 @@ struct alignas(16) NodeA {
     uint32_t counts;             // n_succ | n_bub << 16
     uint32_t symflags;           // symbol | is_exit << 8
 };
+struct alignas(16) BubQ {  // one enclosing superbubble of a node
+    uint32_t exit, min_d, max_d;  // exit node, shortest / longest path length from the node to it
+    uint32_t mde;                 // max(dist_min(exit), 1) - 1: min_dist_to_end used by the prune test (reached.rs:57-58)
+};
 struct alignas(16) NodeB {
     uint32_t dist_min, dist_max;  // shortest / longest path length to `end`
     uint32_t pred_off, n_pred;    // into Graph::pred
 };
-struct alignas(32) NodeRec {
+struct alignas(32) NodeRec {  // one sector per node: everything a visit needs except the adjacency and bubble lists
     NodeA a;
     NodeB b;
 };
@@ -81,7 +105,7 @@ struct Graph {  // node-id space, adjacency in the reference's order
     uint32_t V, start, end;
     const NodeRec *nodes;
     const uint32_t *succ, *pred;
-    const uint32_t *bub;                  // quadruples (exit, min_dist, max_dist, max(dist_min(exit), 1) - 1)
+    const BubQ *bub;                      // enclosing bubbles of every node, innermost first
     const uint32_t *path_off, *path_rem;  // sampled-path remainders for -H path (path_off has V + 1 entries)
 };
 
@@ -90,14 +114,14 @@ struct alignas(16) Item {
 };
 
 struct Scratch {  // one slab per in-flight alignment
-    void *planes;          // three planes (M, D, I) of V * W cells; cell = score | reached-flag (top bit); all-ones-but-top = unvisited
+    void *planes;          // V * W records of CELL_SLOTS cells {M, D, I, pad}; cell = score | reached-flag (top bit); all-ones-but-top = unvisited
     uint32_t *qhead;       // f_max * 3 stack heads (0 = empty, else item index + 1) - authoritative outside the window
     uint32_t *qwin;        // QWIN * 3 heads of priorities [win_base, win_base + QWIN): shared memory on the device
     Item *items;           // max_items
     uint32_t *free_slots;  // max_items: stack of recycled item slots (its top stays cache-hot, unlike a list threaded through items)
     uint32_t *rb;          // per node [lo, hi + 1] of the reached offsets (hi + 1 == 0: none)
     uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
-    uint64_t plane_elems;  // V * W
+    uint64_t plane_elems;  // V * W (records)
     uint32_t W, max_items, f_max;
 };
 
@@ -115,123 +139,119 @@ struct Result {
 };
 
 template <typename CellT> struct CellTraits;
+// CHECK_WRAP: the reference's NonMaxU32 arithmetic panics when a score reaches u32::MAX. The host picks 16-bit cells only
+// when every reachable score stays below 0x7F00, so that instantiation needs none of those tests in its hot loop.
 template <> struct CellTraits<uint16_t> {
     static constexpr uint16_t FLAG = 0x8000u, CUNV = 0x7FFFu;
+    static constexpr bool CHECK_WRAP = false;
 };
 template <> struct CellTraits<uint32_t> {
     static constexpr uint32_t FLAG = 0x80000000u, CUNV = 0x7FFFFFFFu;
+    static constexpr bool CHECK_WRAP = true;
 };
 
 // ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) -----------------------------------------------
 // Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped (the reference would panic).
 template <typename CellT>
 struct PruneCtx {
-    const CellT *m_plane;  // Match plane, V * W
+    const CellT *m_plane;  // the visited table; Match cell of (node, off) at (node * W + off) * CELL_STRIDE
     const uint32_t *rb;    // reached bounds per node
-    const uint32_t *bub;
     uint32_t W, Q, o, e;
 };
 
+// can_improve_bubble for one bubble; true = the state can still improve on it (no prune from this bubble)
 template <typename CellT>
-RP_HD int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_end, uint32_t node, uint32_t off, uint32_t st,
-                     uint32_t score) {
+RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, uint32_t off, uint32_t st, uint32_t score,
+                        bool &wrapped) {
     constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
-    bool wrapped = false;
-    auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
-    // issue the loads every bubble will need (reached bounds and the exit's Match row around the target offset) before
-    // evaluating any of them, so their DRAM latencies overlap instead of adding up
-    for (uint32_t k = bub_begin; k < bub_end; ++k) {
-        const uint32_t exit = c.bub[4 * k];
-        RP_PREFETCH(c.rb + 2 * (size_t)exit);
-        RP_PREFETCH(c.m_plane + (size_t)exit * c.W + off + c.bub[4 * k + 1]);
+    RP_CNT(C_PRUNE_BUB);
+    if (node == b.exit || off + b.max_d > c.Q) return true;
+    const uint32_t lo = c.rb[2 * (size_t)b.exit], hi1 = c.rb[2 * (size_t)b.exit + 1], mde = b.mde;
+    if (hi1 == 0) {  // no offset reached at this exit yet
+        RP_CNT(C_PRUNE_NOREACH);
+        return true;
     }
-    for (uint32_t k = bub_begin; k < bub_end; ++k) {
-        const uint32_t exit = c.bub[4 * k], min_d = c.bub[4 * k + 1], max_d = c.bub[4 * k + 2], mde = c.bub[4 * k + 3];
-        const uint32_t lo = c.rb[2 * exit], hi1 = c.rb[2 * exit + 1];
-        if (hi1 == 0) continue;  // no offset reached at this exit yet: can improve
-        if (node == exit) continue;
-        const uint32_t tmin = off + min_d, tmax = off + max_d;
-        if (tmax > c.Q) continue;
-        const CellT *mrow = c.m_plane + (size_t)exit * c.W;
-        // reached offsets = Match cells of the exit row with the flag bit; scans stay inside [lo, hi]
-        auto prev_of = [&](uint32_t lim) -> uint32_t {  // largest reached offset < lim
-            if (lim <= lo) return UNV;
-            uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
-            for (;;) {
-                if (mrow[i] & FLAG) return i;
-                if (i == lo) return UNV;
-                --i;
-            }
-        };
-        auto next_of = [&](uint32_t lim) -> uint32_t {  // smallest reached offset >= lim
-            if (lim >= hi1) return UNV;
-            uint32_t i = lim < lo ? lo : lim;
-            for (;;) {
-                if (mrow[i] & FLAG) return i;
-                if (++i >= hi1) return UNV;
-            }
-        };
-        auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
-            const CellT v = (CellT)(mrow[r] & (CellT)~FLAG);
-            if (v == CUNV) wrapped = true;
-            const uint32_t t = (uint32_t)v + plus;
-            if (t == UNV) wrapped = true;
-            return t;
-        };
-        auto improve_at = [&](uint32_t x, uint32_t left, uint32_t right) -> bool {  // reached.rs:191-255
-            uint32_t implicit;
-            if (left != UNV && right != UNV) {
-                const uint32_t il = S(left, gap(x - left));
-                const uint32_t gr = right - x;
-                const uint32_t ir = S(right, gap(gr));
-                implicit = gr > mde ? il : (il < ir ? il : ir);
-            } else if (right != UNV) {
-                const uint32_t gr = right - x;
-                const uint32_t ir = S(right, gap(gr));
-                if (gr > mde) return true;
-                implicit = ir;
-            } else if (left != UNV) {
-                implicit = S(left, gap(x - left));
-            } else {
-                return true;
-            }
-            return score < implicit;
-        };
-        bool can = false;
-        uint32_t prev = prev_of(tmin);
-        bool have_last = false;
-        uint32_t last = 0;
-        for (uint32_t nx = next_of(tmin); nx != UNV && nx <= tmax; nx = next_of(nx + 1)) {
-            const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
-            if (st == ST_D && S(nx, c.o) > score) {
-                can = true;
-                break;
-            }
-            if (prev != UNV && st == ST_I && S(prev, c.o) > score) {
-                can = true;
-                break;
-            }
-            if (improve_at(o1, prev, nx)) {
-                can = true;
-                break;
-            }
-            uint32_t o2 = nx - 1u;  // wraps for nx == 0 like the release build
-            if (o2 < tmin) o2 = tmin;
-            if (o2 > tmax) o2 = tmax;
-            if (o2 != o1 && improve_at(o2, prev, nx)) {
-                can = true;
-                break;
-            }
-            prev = nx;
-            last = o2;
-            have_last = true;
+    auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
+    const uint32_t tmin = off + b.min_d, tmax = off + b.max_d;
+    const CellT *mrow = c.m_plane + (size_t)b.exit * c.W * CELL_STRIDE;
+    auto at = [&](uint32_t i) -> CellT {  // Match cell of the exit row
+        RP_CNT(C_PRUNE_PROBE);
+        return mrow[i * CELL_STRIDE];
+    };
+    // reached offsets = Match cells of the exit row with the flag bit; scans stay inside [lo, hi]
+    auto prev_of = [&](uint32_t lim) -> uint32_t {  // largest reached offset < lim
+        if (lim <= lo) return UNV;
+        uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
+        for (;;) {
+            if (at(i) & FLAG) return i;
+            if (i == lo) return UNV;
+            --i;
         }
-        if (!can) {
-            const uint32_t next = next_of(tmax == UNV ? tmax : tmax + 1);
-            if (!have_last && improve_at(tmin, prev, next)) can = true;
-            else if ((!have_last || last < tmax) && improve_at(tmax, prev, next)) can = true;
-            else if (prev != UNV && st == ST_I && S(prev, c.o) > score) can = true;
+    };
+    auto next_of = [&](uint32_t lim) -> uint32_t {  // smallest reached offset >= lim
+        if (lim >= hi1) return UNV;
+        uint32_t i = lim < lo ? lo : lim;
+        for (;;) {
+            if (at(i) & FLAG) return i;
+            if (++i >= hi1) return UNV;
         }
+    };
+    auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
+        const CellT v = (CellT)(at(r) & (CellT)~FLAG);
+        RP_CNT(C_PRUNE_SCORE);
+        const uint32_t t = (uint32_t)v + plus;
+        if (CellTraits<CellT>::CHECK_WRAP && (v == CUNV || t == UNV)) wrapped = true;
+        return t;
+    };
+    auto improve_at = [&](uint32_t x, uint32_t left, uint32_t right) -> bool {  // reached.rs:191-255
+        uint32_t implicit;
+        if (left != UNV && right != UNV) {
+            const uint32_t il = S(left, gap(x - left));
+            const uint32_t gr = right - x;
+            const uint32_t ir = S(right, gap(gr));
+            implicit = gr > mde ? il : (il < ir ? il : ir);
+        } else if (right != UNV) {
+            const uint32_t gr = right - x;
+            const uint32_t ir = S(right, gap(gr));
+            if (gr > mde) return true;
+            implicit = ir;
+        } else if (left != UNV) {
+            implicit = S(left, gap(x - left));
+        } else {
+            return true;
+        }
+        return score < implicit;
+    };
+    uint32_t prev = prev_of(tmin);
+    bool have_last = false;
+    uint32_t last = 0;
+    for (uint32_t nx = next_of(tmin); nx != UNV && nx <= tmax; nx = next_of(nx + 1)) {
+        const uint32_t o1 = prev != UNV ? (tmin > prev + 1 ? tmin : prev + 1) : tmin;
+        if (st == ST_D && S(nx, c.o) > score) return true;
+        if (prev != UNV && st == ST_I && S(prev, c.o) > score) return true;
+        if (improve_at(o1, prev, nx)) return true;
+        uint32_t o2 = nx - 1u;  // wraps for nx == 0 like the release build
+        if (o2 < tmin) o2 = tmin;
+        if (o2 > tmax) o2 = tmax;
+        if (o2 != o1 && improve_at(o2, prev, nx)) return true;
+        prev = nx;
+        last = o2;
+        have_last = true;
+    }
+    const uint32_t next = next_of(tmax == UNV ? tmax : tmax + 1);
+    if (!have_last && improve_at(tmin, prev, next)) return true;
+    if ((!have_last || last < tmax) && improve_at(tmax, prev, next)) return true;
+    if (prev != UNV && st == ST_I && S(prev, c.o) > score) return true;
+    return false;
+}
+
+// All bubbles of a node, innermost first (index.rs order); one 128-bit load per quadruple.
+template <typename CellT>
+RP_HD int prune_eval(const PruneCtx<CellT> &c, const BubQ *bubs, uint32_t n_bub, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+    bool wrapped = false;
+    for (uint32_t k = 0; k < n_bub; ++k) {
+        const BubQ b = bubs[k];
+        const bool can = prune_bubble<CellT>(c, b, node, off, st, score, wrapped);
         if (wrapped) return 2;
         if (!can) return 1;  // !all(can_improve)
     }
@@ -243,6 +263,7 @@ RP_HD int prune_eval(const PruneCtx<CellT> c, uint32_t bub_begin, uint32_t bub_e
 template <typename CellT>
 struct Search {
     static constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
+    static constexpr bool CHECK_WRAP = CellTraits<CellT>::CHECK_WRAP;
     const Graph &g;
     const uint8_t *q;
     const uint32_t Q;
@@ -265,7 +286,11 @@ struct Search {
 
     // ---- visited table -------------------------------------------------------------------------
     RP_HD CellT *cell(uint32_t node, uint32_t off, uint32_t st) const {
+#if defined(RP_PLANAR)
         return static_cast<CellT *>(s.planes) + (size_t)st * s.plane_elems + (size_t)node * s.W + off;
+#else
+        return static_cast<CellT *>(s.planes) + ((size_t)node * s.W + off) * CELL_STRIDE + st;
+#endif
     }
     RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
         const CellT v = (CellT)(*cell(node, off, st) & (CellT)~FLAG);
@@ -273,15 +298,33 @@ struct Search {
     }
     RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) { *cell(node, off, st) = (CellT)v; }
     RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
-        if (v >= (uint32_t)CUNV) {  // cannot happen when the host sized CellT correctly
+        if (CHECK_WRAP && v >= (uint32_t)CUNV) {  // cannot happen when the host sized CellT correctly
             err = RP_SCORE_WRAP;
             return false;
         }
         CellT *c = cell(node, off, st);
         const CellT cur = *c;
         const CellT curv = (CellT)(cur & (CellT)~FLAG);
+        RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
+            RP_CNT(C_RELAX_OK);
             *c = (CellT)((CellT)v | (CellT)(cur & FLAG));  // a reached offset stays reached when its score improves
+            return true;
+        }
+        return false;
+    }
+
+    // relax() on a cell whose current value `cur` was loaded earlier (together with other loads) and not written since
+    RP_HD bool relax_loaded(CellT *c, CellT cur, uint32_t v) {
+        if (CHECK_WRAP && v >= (uint32_t)CUNV) {
+            err = RP_SCORE_WRAP;
+            return false;
+        }
+        const CellT curv = (CellT)(cur & (CellT)~FLAG);
+        RP_CNT(C_RELAX);
+        if (curv == CUNV || v < (uint32_t)curv) {
+            RP_CNT(C_RELAX_OK);
+            *c = (CellT)((CellT)v | (CellT)(cur & FLAG));
             return true;
         }
         return false;
@@ -289,9 +332,8 @@ struct Search {
 
     // ---- score arithmetic with the reference's NonMaxU32 / wrapping behaviour -------------------------
     RP_HD uint32_t add(uint32_t a, uint32_t b) {
-        if (a == UNV) err = RP_SCORE_WRAP;
         const uint32_t r = a + b;
-        if (r == UNV) err = RP_SCORE_WRAP;
+        if (CHECK_WRAP && (a == UNV || r == UNV)) err = RP_SCORE_WRAP;
         return r;
     }
     RP_HD uint32_t sub(uint32_t a, uint32_t b) {
@@ -335,6 +377,7 @@ struct Search {
     RP_HD void move_window(uint32_t f) {  // make [f & ~63, +64) the fast window
         const uint32_t nb = f & ~(QWIN - 1);
         if (nb == win_base) return;
+        RP_CNT(C_WINDOW_MOVE);
         for (uint32_t i = 0; i < QWIN * 3; ++i) {
             const uint32_t fo = win_base * 3 + i, fn = nb * 3 + i;
             if (fo < s.f_max * 3) s.qhead[fo] = s.qwin[i];
@@ -344,6 +387,7 @@ struct Search {
     }
     RP_HD void push(uint32_t node, uint32_t dist_min, uint32_t dist_max, uint32_t off, uint32_t st, uint32_t score) {
         RP_T0;
+        RP_CNT(C_PUSH);
         const uint32_t f = score + h(node, dist_min, dist_max, off, st);
         if (f >= s.f_max) {
             err = RP_PRIORITY_RANGE;
@@ -376,6 +420,7 @@ struct Search {
         for (;;) {
             if (f_cur - win_base >= QWIN) move_window(f_cur);
             uint32_t *head = head_ptr(f_cur);
+            RP_CNT(C_POP_SCAN);
             for (uint32_t k = 0; k < 3; ++k) {  // Match, then Deletion, then Insertion
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
@@ -412,8 +457,9 @@ struct Search {
         const uint32_t nb = a.counts >> 16;
         if (nb == 0) return false;
         RP_T0;
-        PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, g.bub, s.W, Q, p.o, p.e};
-        const int r = prune_eval<CellT>(c, a.bub_off, a.bub_off + nb, node, off, st, score);
+        RP_CNT(C_PRUNE_CALL);
+        const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
+        const int r = prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
         RP_ACC(prof_prune);
 #if defined(RP_PROFILE)
@@ -502,15 +548,23 @@ struct Search {
                 err = RP_EMPTY_QUEUE;
                 break;
             }
-            RP_PREFETCH(g.nodes + it.node);
-            if (it.score > get(it.node, it.offset, st)) continue;
+            // the state's own cell (stale test) and its node record, issued as one group of loads
+            const CellT own = *cell(it.node, it.offset, st);
+            const NodeA na = node_a(it.node);
+            const NodeB nb = node_b(it.node);
+            const uint32_t n_succ = na.counts & 0xFFFF;
+            {
+                const CellT ownv = (CellT)(own & (CellT)~FLAG);
+                if (ownv != CUNV && it.score > (uint32_t)ownv) {
+                    RP_CNT(C_POP_STALE);
+                    continue;
+                }
+            }
             if (is_end(it.node, it.offset, st)) {
                 ++res.num_visited;
                 end_score = it.score, end_node = it.node, end_off = it.offset;
                 break;
             }
-            const NodeA na = node_a(it.node);
-            const NodeB nb = node_b(it.node);
             if (prune(it.score, it.node, na, it.offset, st)) {
                 ++res.num_pruned;
                 continue;
@@ -518,37 +572,40 @@ struct Search {
             mark_reached(it.node, (na.symflags >> 8) & 1, it.offset, st);
             ++res.num_visited;
             const uint32_t score = it.score;
+            if (st == ST_M) RP_CNT(C_POP_M);
+            else if (st == ST_D) RP_CNT(C_POP_D);
+            else RP_CNT(C_POP_I);
             if (st == ST_M) {
-                // depth-first greedy match extension (dfa.rs:138-250)
+                // depth-first greedy match extension (dfa.rs:138-250). The top frame lives in registers; s.dfa holds the
+                // frames below it (most extensions stop after one or two nodes and never touch it).
                 uint32_t depth = 1;
                 uint32_t *F = s.dfa;
-                F[0] = it.node, F[1] = it.offset, F[2] = na.succ_off, F[3] = na.succ_off + (na.counts & 0xFFFF);
-                F[4] = nb.dist_min, F[5] = nb.dist_max;
+                uint32_t t_node = it.node, t_off = it.offset, t_k = na.succ_off, t_end = na.succ_off + n_succ;
+                uint32_t t_dmin = nb.dist_min, t_dmax = nb.dist_max;
                 uint32_t dfa_visited = 0;
                 while (depth > 0 && err == RP_OK) {
                     // offset-0 special case, evaluated on every resume while a single frame is on the stack (dfa.rs:145-168)
                     bool virtual_end = false;
                     uint32_t v_parent = 0;
-                    if (depth == 1 && Q != 0 && F[1] == 0 && sym_eq(F[0], na, q[0])) {
-                        if (relax(F[0], 1, ST_M, score)) {
-                            v_parent = F[0];
-                            F[1] = 1, F[2] = na.succ_off;
-                            mark_reached(F[0], (na.symflags >> 8) & 1, 1, ST_M);
+                    if (depth == 1 && Q != 0 && t_off == 0 && sym_eq(t_node, na, q[0])) {
+                        if (relax(t_node, 1, ST_M, score)) {
+                            v_parent = t_node;
+                            t_off = 1, t_k = na.succ_off;
+                            mark_reached(t_node, (na.symflags >> 8) & 1, 1, ST_M);
                             ++dfa_visited;
                             if (Q == 1) virtual_end = true;
                         }
                     }
                     int kind = 0;  // 0 exhausted, 1 ref-graph end, 2 query end, 3 match, 4 mismatch
-                    uint32_t pn, po, pdmin, pdmax, cn = 0, co = 0;
+                    uint32_t pn = t_node, po = t_off, cn = 0, co = 0;
+                    const uint32_t pdmin = t_dmin, pdmax = t_dmax;
                     NodeA ca{0, 0, 0, 0};
-                    uint32_t *fr = F + (size_t)(depth - 1) * 6;
-                    pn = fr[0], po = fr[1], pdmin = fr[4], pdmax = fr[5];
+                    NodeB cb{0, 0, 0, 0};
                     if (virtual_end) {
                         kind = 1, pn = v_parent, po = 0, cn = v_parent, co = 1;
                     } else {
-                        const uint32_t se = fr[3];
-                        while (fr[2] < se) {
-                            const uint32_t child = g.succ[fr[2]++];
+                        while (t_k < t_end) {
+                            const uint32_t child = g.succ[t_k++];
                             if (child == g.end) {
                                 relax(child, po, ST_M, score);
                                 kind = 1, cn = child, co = po;
@@ -558,31 +615,39 @@ struct Search {
                                 kind = 2, cn = child;
                                 break;
                             }
-                            RP_PREFETCH(cell(child, po + 1, ST_M));  // needed right after the symbol test; overlaps the record load
+                            // the child's cell and its record in one group of loads
+                            CellT *cc = cell(child, po + 1, ST_M);
+                            const CellT ccur = *cc;
                             ca = node_a(child);
-                            RP_PREFETCH(g.bub + 4 * (size_t)ca.bub_off);
-                            RP_PREFETCH(g.succ + ca.succ_off);
+                            cb = node_b(child);
+                            RP_CNT(C_DFA_STEP);
                             if ((ca.symflags & 0xFF) == q[po]) {
-                                if (relax(child, po + 1, ST_M, score)) {
+                                if (relax_loaded(cc, ccur, score)) {
+                                    RP_CNT(C_DFA_MATCH);
                                     kind = 3, cn = child, co = po + 1;
                                     break;
                                 }
+                                RP_CNT(C_DFA_RELAX_FAIL);
                             } else {
+                                RP_CNT(C_DFA_MISMATCH);
                                 kind = 4, cn = child, co = po + 1;
                                 break;
                             }
                         }
                     }
                     if (kind == 0) {
-                        --depth;
+                        if (--depth > 0) {
+                            const uint32_t *fr = F + (size_t)(depth - 1) * 6;
+                            t_node = fr[0], t_off = fr[1], t_k = fr[2], t_end = fr[3], t_dmin = fr[4], t_dmax = fr[5];
+                        }
                     } else if (kind == 3) {
                         if (prune(score, cn, ca, co, ST_M)) continue;
                         mark_reached(cn, (ca.symflags >> 8) & 1, co, ST_M);
                         ++dfa_visited;
-                        const NodeB cb = node_b(cn);
-                        uint32_t *nf = F + (size_t)depth * 6;
-                        nf[0] = cn, nf[1] = co, nf[2] = ca.succ_off, nf[3] = ca.succ_off + (ca.counts & 0xFFFF);
-                        nf[4] = cb.dist_min, nf[5] = cb.dist_max;
+                        uint32_t *fr = F + (size_t)(depth - 1) * 6;  // spill the frame that stops being the top
+                        fr[0] = t_node, fr[1] = t_off, fr[2] = t_k, fr[3] = t_end, fr[4] = t_dmin, fr[5] = t_dmax;
+                        t_node = cn, t_off = co, t_k = ca.succ_off, t_end = ca.succ_off + (ca.counts & 0xFFFF);
+                        t_dmin = cb.dist_min, t_dmax = cb.dist_max;
                         ++depth;
                     } else if (kind == 1) {
                         if (is_end(cn, co, ST_M)) {
@@ -596,12 +661,11 @@ struct Search {
                         }
                     } else if (kind == 2) {
                         if (relax(cn, po, ST_D, add(add(score, p.o), p.e))) {  // gap_affine.rs:369-391
-                            const NodeB cb = node_b(cn);
+                            cb = node_b(cn);
                             push(cn, cb.dist_min, cb.dist_max, po, ST_D, add(score, oe8));
                             ++res.num_queued;
                         }
                     } else {  // mismatch: gap_affine.rs:393-430
-                        const NodeB cb = node_b(cn);
                         if (relax(cn, co, ST_M, add(score, p.x))) {
                             push(cn, cb.dist_min, cb.dist_max, co, ST_M, add(score, p.x));
                             ++res.num_queued;
@@ -632,11 +696,13 @@ struct Search {
                     push(it.node, nb.dist_min, nb.dist_max, it.offset, ST_M, score);
                     ++res.num_queued;
                 }
-                const uint32_t se = na.succ_off + (na.counts & 0xFFFF);
+                const uint32_t se = na.succ_off + n_succ;
                 for (uint32_t k = na.succ_off; k < se; ++k) {
                     const uint32_t c = g.succ[k];
-                    if (relax(c, it.offset, ST_D, add(score, p.e))) {
-                        const NodeB cb = node_b(c);
+                    CellT *cc = cell(c, it.offset, ST_D);
+                    const CellT ccur = *cc;
+                    const NodeB cb = node_b(c);  // loaded with the cell, used only when the relaxation succeeds
+                    if (relax_loaded(cc, ccur, add(score, p.e))) {
                         push(c, cb.dist_min, cb.dist_max, it.offset, ST_D, add(score, p.e));
                         ++res.num_queued;
                     }

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             const uint32_t pat = sizeof(CellT) == 2 ? 0x7FFF7FFFu : 0x7FFFFFFFu;
             const uint4 unv = make_uint4(pat, pat, pat, pat), z = make_uint4(0, 0, 0, 0);
             uint4 *p0 = reinterpret_cast<uint4 *>(slab);
-            const uint64_t n0 = ((uint64_t)3 * gd.V * dims.W * sizeof(CellT) + 15) / 16;
+            const uint64_t n0 = ((uint64_t)replay::CELL_SLOTS * gd.V * dims.W * sizeof(CellT) + 15) / 16;
             for (uint64_t i = lane; i < n0; i += 32) p0[i] = unv;
             uint4 *p1 = reinterpret_cast<uint4 *>(slab + B.off_qhead);
             const uint32_t n1 = ((uint64_t)dims.f_max * 3 + 3) / 4;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             g.nodes = B.nodes + gd.node_base;
             g.succ = B.succ + gd.succ_base;
             g.pred = B.pred + gd.pred_base;
-            g.bub = B.bub + (uint64_t)gd.bub_base * 4;
+            g.bub = reinterpret_cast<const replay::BubQ *>(B.bub) + gd.bub_base;
             g.path_off = B.path_off + gd.pathoff_base;
             g.path_rem = B.path_rem + gd.path_base;
             replay::Scratch s;

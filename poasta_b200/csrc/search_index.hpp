@@ -26,6 +26,7 @@ struct SearchIndex {
 
     // 32-byte node records of the search kernel (replay_core.hpp); offsets are relative to the graph's own arrays
     void node_records(const poasta_graph_view &v, std::vector<replay::NodeRec> &out) const {
+        out.reserve(out.size() + v.n_nodes);
         for (uint32_t n = 0; n < v.n_nodes; ++n) {
             replay::NodeRec r;
             r.a.succ_off = v.succ_off[n];
