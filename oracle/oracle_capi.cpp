@@ -322,15 +322,18 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
     Result r;
     uint32_t used_blocks = 0, used_items = 0;
-    if (cell16) {
-        rp::Search<uint16_t> search(g, seq, qlen, p, s);
+    auto go = [&](auto cell, auto heur) {
+        rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
         r = search.run(out_r.data(), out_q.data(), ocap);
         used_items = search.n_items;
-    } else {
-        rp::Search<uint32_t> search(g, seq, qlen, p, s);
-        r = search.run(out_r.data(), out_q.data(), ocap);
-        used_items = search.n_items;
-    }
+    };
+    auto go_cell = [&](auto cell) {
+        if (heuristic == 0) go(cell, std::integral_constant<int, 0>{});
+        else if (heuristic == 1) go(cell, std::integral_constant<int, 1>{});
+        else go(cell, std::integral_constant<int, 2>{});
+    };
+    if (cell16) go_cell(uint16_t{});
+    else go_cell(uint32_t{});
     *score = r.score;
     *n_pairs = r.n_pairs;
     for (uint32_t i = 0; i < r.n_pairs && i < cap; ++i) {

@@ -799,17 +799,23 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
 
     CK(cudaEventRecord(c.ev0, s));
     {
-        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 14;
+        // MINB = resident CTAs per SM the register allocation must allow: 16 -> 64 registers, no spills, 32 warps per SM
+        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 16;
         const dim3 grid((unsigned)(workers / warps_per_cta)), block(warps_per_cta * 32);
-        if (cell16) {
-            if (minb >= 32) replay_kernel<uint16_t, 32><<<grid, block, 0, s>>>(B);
-            else if (minb >= 24) replay_kernel<uint16_t, 24><<<grid, block, 0, s>>>(B);
-            else replay_kernel<uint16_t, 14><<<grid, block, 0, s>>>(B);
-        } else {
-            if (minb >= 32) replay_kernel<uint32_t, 32><<<grid, block, 0, s>>>(B);
-            else if (minb >= 24) replay_kernel<uint32_t, 24><<<grid, block, 0, s>>>(B);
-            else replay_kernel<uint32_t, 14><<<grid, block, 0, s>>>(B);
-        }
+        auto launch = [&](auto cell, auto heur) {
+            using CellT = decltype(cell);
+            constexpr int H = decltype(heur)::value;
+            if (minb >= 24) replay_kernel<CellT, 24, H><<<grid, block, 0, s>>>(B);
+            else if (minb >= 16) replay_kernel<CellT, 16, H><<<grid, block, 0, s>>>(B);
+            else replay_kernel<CellT, 14, H><<<grid, block, 0, s>>>(B);
+        };
+        auto launch_cell = [&](auto cell) {
+            if (prm.heuristic == 0) launch(cell, std::integral_constant<int, 0>{});
+            else if (prm.heuristic == 1) launch(cell, std::integral_constant<int, 1>{});
+            else launch(cell, std::integral_constant<int, 2>{});
+        };
+        if (cell16) launch_cell(uint16_t{});
+        else launch_cell(uint32_t{});
     }
     scan_kernel<<<1, 1024, 0, s>>>(B.n_pairs, (uint32_t *)c.offsets.d, n);
     CK(cudaEventRecord(c.ev1, s));
@@ -847,6 +853,14 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     res.dense_r = (const uint32_t *)c.h_dense_r.h;
     res.dense_q = (const uint32_t *)c.h_dense_q.h;
     if (stats_out) stats_out->assign((uint32_t *)c.h_stats.h, (uint32_t *)c.h_stats.h + (size_t)n * 4);
+    static const bool timing = getenv("POASTA_TIMING") != nullptr;
+    if (timing) {  // a launch lasts as long as its slowest alignment: show how uneven the alignments of one launch are
+        const uint32_t *st = (const uint32_t *)c.h_stats.h;
+        uint64_t sum = 0, mx = 0;
+        for (size_t i = 0; i < n; ++i) sum += st[4 * i + 1], mx = std::max<uint64_t>(mx, st[4 * i + 1]);
+        fprintf(stderr, "poasta_b200 lane %d: search launch of %zu alignments, %u workers, %.1f ms; visited states mean %.0f max %llu\n", tl_lane,
+                (size_t)n, (unsigned)workers, ms, (double)sum / (double)n, (unsigned long long)mx);
+    }
     return 0;
 }
 
@@ -1142,7 +1156,9 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
     int lanes = 1;
     if (const char *e = getenv("POASTA_LANES")) lanes = std::max(1, std::min(MAX_LANES, atoi(e)));
     else lanes = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, n_families / 256));
-    const unsigned threads_per_lane = std::max(1u, std::min(64u, hw) / lanes);
+    // host phases of different lanes rarely coincide (the others wait on their kernels), so lanes share the cores generously
+    unsigned threads_per_lane = std::max(1u, std::min(64u, hw) / lanes);
+    if (const char *e = getenv("POASTA_THREADS_PER_LANE")) threads_per_lane = std::max(1, atoi(e));
     struct LaneOut {
         int rc = 0;
         uint64_t cells = 0, h2d = 0, d2h = 0;

@@ -260,7 +260,9 @@ RP_HD int prune_eval(const PruneCtx<CellT> &c, const BubQ *bubs, uint32_t n_bub,
 
 // CellT = uint16_t halves the table footprint (more alignments in flight); the host picks it only when the largest
 // possible score (every node deleted + every query base inserted) is below 0x7F00.
-template <typename CellT>
+// HEUR = Params::heuristic as a compile-time constant: every push evaluates h(), and the three heuristics inlined at every
+// push site tripled the kernel's code size (instruction-cache misses were 20-30 % of its stall cycles).
+template <typename CellT, int HEUR>
 struct Search {
     static constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
     static constexpr bool CHECK_WRAP = CellTraits<CellT>::CHECK_WRAP;
@@ -348,25 +350,27 @@ struct Search {
 
     // ---- heuristic (dist = the node's distances to `end`) -----------------------------------------------
     RP_HD uint32_t h(uint32_t node, uint32_t dist_min, uint32_t dist_max, uint32_t off, uint32_t st) const {
-        if (p.heuristic == 0) return 0;
-        if (p.heuristic == 1) {
+        if constexpr (HEUR == 0) {
+            return 0;
+        } else if constexpr (HEUR == 1) {
             const uint32_t tmin = off + (dist_min ? dist_min - 1 : 0), tmax = off + (dist_max ? dist_max - 1 : 0);
             if (tmin > Q) return gap_cost(st == ST_D ? ST_D : ST_M, tmin - Q);
             if (tmax < Q) return gap_cost(st == ST_I ? ST_I : ST_M, Q - tmax);
             return 0;
+        } else {
+            const uint32_t rem_q = Q > off ? Q - off : 0;
+            const uint32_t b = g.path_off[node], e = g.path_off[node + 1];
+            if (b == e) return gap_cost(st, rem_q);
+            uint32_t best = UNV;
+            for (uint32_t k = b; k < e; ++k) {
+                const uint32_t rem_p = g.path_rem[k];
+                uint32_t c = 0;
+                if (rem_p > rem_q) c = gap_cost(st == ST_D ? ST_D : ST_M, rem_p - rem_q);
+                else if (rem_q > rem_p) c = gap_cost(st == ST_I ? ST_I : ST_M, rem_q - rem_p);
+                if (c < best) best = c;
+            }
+            return best;
         }
-        const uint32_t rem_q = Q > off ? Q - off : 0;
-        const uint32_t b = g.path_off[node], e = g.path_off[node + 1];
-        if (b == e) return gap_cost(st, rem_q);
-        uint32_t best = UNV;
-        for (uint32_t k = b; k < e; ++k) {
-            const uint32_t rem_p = g.path_rem[k];
-            uint32_t c = 0;
-            if (rem_p > rem_q) c = gap_cost(st == ST_D ? ST_D : ST_M, rem_p - rem_q);
-            else if (rem_q > rem_p) c = gap_cost(st == ST_I ? ST_I : ST_M, rem_q - rem_p);
-            if (c < best) best = c;
-        }
-        return best;
     }
 
     // ---- bucket queue ---------------------------------------------------------------------------------
@@ -575,15 +579,34 @@ struct Search {
             if (st == ST_M) RP_CNT(C_POP_M);
             else if (st == ST_D) RP_CNT(C_POP_D);
             else RP_CNT(C_POP_I);
-            if (st == ST_M) {
-                // depth-first greedy match extension (dfa.rs:138-250). The top frame lives in registers; s.dfa holds the
-                // frames below it (most extensions stop after one or two nodes and never touch it).
-                uint32_t depth = 1;
-                uint32_t *F = s.dfa;
-                uint32_t t_node = it.node, t_off = it.offset, t_k = na.succ_off, t_end = na.succ_off + n_succ;
-                uint32_t t_dmin = nb.dist_min, t_dmax = nb.dist_max;
-                uint32_t dfa_visited = 0;
-                while (depth > 0 && err == RP_OK) {
+            // Every expansion ends in "relax, and queue if improved" steps in a fixed order. They are collected as up to three
+            // transitions (plus the per-successor deletions of a popped D state) and applied at ONE place below, so the
+            // queue / heuristic code exists once in the kernel instead of at a dozen inlined sites.
+            //   Match: depth-first greedy match extension (dfa.rs:138-250), transitions per run end (gap_affine.rs:346-430).
+            //          The top frame lives in registers; s.dfa holds the frames below it (most extensions stop after one
+            //          or two nodes and never touch it).
+            //   Insertion / Deletion: one pass through the same loop (gap_affine.rs:307-341).
+            uint32_t depth = st == ST_M ? 1u : 0u;
+            bool single_pass = st != ST_M;
+            uint32_t *F = s.dfa;
+            uint32_t t_node = it.node, t_off = it.offset, t_k = na.succ_off, t_end = na.succ_off + n_succ;
+            uint32_t t_dmin = nb.dist_min, t_dmax = nb.dist_max;
+            uint32_t dfa_visited = 0;
+            const uint32_t open_score = add(add(score, p.o), p.e), open_queued = add(score, oe8);
+            while ((depth > 0 || single_pass) && err == RP_OK) {
+                // transitions of this pass: (node, offset, state, relaxed score); `gap-open` ones are queued with open_queued
+                uint32_t nt = 0, tn0 = 0, to0 = 0, ts0 = 0, tv0 = 0, tn1 = 0, to1 = 0, ts1 = 0, tv1 = 0, tn2 = 0, to2 = 0, ts2 = 0, tv2 = 0;
+                uint32_t open_mask = 0;        // bit i: transition i opens a gap
+                uint32_t dk = 0, dk_end = 0;   // successor range whose Deletion states follow the listed transitions
+                if (single_pass) {
+                    single_pass = false;
+                    tn0 = it.node, to0 = it.offset, ts0 = ST_M, tv0 = score, nt = 1;  // close the gap
+                    if (st == ST_I) {
+                        if (it.offset < Q) tn1 = it.node, to1 = it.offset + 1, ts1 = ST_I, tv1 = add(score, p.e), nt = 2;
+                    } else {
+                        dk = na.succ_off, dk_end = na.succ_off + n_succ;
+                    }
+                } else {
                     // offset-0 special case, evaluated on every resume while a single frame is on the stack (dfa.rs:145-168)
                     bool virtual_end = false;
                     uint32_t v_parent = 0;
@@ -598,7 +621,6 @@ struct Search {
                     }
                     int kind = 0;  // 0 exhausted, 1 ref-graph end, 2 query end, 3 match, 4 mismatch
                     uint32_t pn = t_node, po = t_off, cn = 0, co = 0;
-                    const uint32_t pdmin = t_dmin, pdmax = t_dmax;
                     NodeA ca{0, 0, 0, 0};
                     NodeB cb{0, 0, 0, 0};
                     if (virtual_end) {
@@ -640,7 +662,9 @@ struct Search {
                             const uint32_t *fr = F + (size_t)(depth - 1) * 6;
                             t_node = fr[0], t_off = fr[1], t_k = fr[2], t_end = fr[3], t_dmin = fr[4], t_dmax = fr[5];
                         }
-                    } else if (kind == 3) {
+                        continue;
+                    }
+                    if (kind == 3) {
                         if (prune(score, cn, ca, co, ST_M)) continue;
                         mark_reached(cn, (ca.symflags >> 8) & 1, co, ST_M);
                         ++dfa_visited;
@@ -649,65 +673,48 @@ struct Search {
                         t_node = cn, t_off = co, t_k = ca.succ_off, t_end = ca.succ_off + (ca.counts & 0xFFFF);
                         t_dmin = cb.dist_min, t_dmax = cb.dist_max;
                         ++depth;
-                    } else if (kind == 1) {
+                        continue;
+                    }
+                    if (kind == 1) {
                         if (is_end(cn, co, ST_M)) {
                             end_score = score, end_node = cn, end_off = co;
                             done = true;
                             break;
                         }
-                        if (relax(pn, po + 1, ST_I, add(add(score, p.o), p.e))) {  // gap_affine.rs:346-367
-                            push(pn, pdmin, pdmax, po + 1, ST_I, add(score, oe8));
-                            ++res.num_queued;
-                        }
+                        tn0 = pn, to0 = po + 1, ts0 = ST_I, tv0 = open_score, open_mask = 1, nt = 1;  // gap_affine.rs:346-367
                     } else if (kind == 2) {
-                        if (relax(cn, po, ST_D, add(add(score, p.o), p.e))) {  // gap_affine.rs:369-391
-                            cb = node_b(cn);
-                            push(cn, cb.dist_min, cb.dist_max, po, ST_D, add(score, oe8));
-                            ++res.num_queued;
-                        }
+                        tn0 = cn, to0 = po, ts0 = ST_D, tv0 = open_score, open_mask = 1, nt = 1;  // gap_affine.rs:369-391
                     } else {  // mismatch: gap_affine.rs:393-430
-                        if (relax(cn, co, ST_M, add(score, p.x))) {
-                            push(cn, cb.dist_min, cb.dist_max, co, ST_M, add(score, p.x));
-                            ++res.num_queued;
-                        }
-                        const uint32_t ns = add(add(score, p.o), p.e);
-                        if (relax(pn, po + 1, ST_I, ns)) {
-                            push(pn, pdmin, pdmax, po + 1, ST_I, add(score, oe8));
-                            ++res.num_queued;
-                        }
-                        if (relax(cn, po, ST_D, ns)) {
-                            push(cn, cb.dist_min, cb.dist_max, po, ST_D, add(score, oe8));
-                            ++res.num_queued;
-                        }
+                        tn0 = cn, to0 = co, ts0 = ST_M, tv0 = add(score, p.x);
+                        tn1 = pn, to1 = po + 1, ts1 = ST_I, tv1 = open_score;
+                        tn2 = cn, to2 = po, ts2 = ST_D, tv2 = open_score;
+                        open_mask = 6, nt = 3;
                     }
                 }
-                if (!done) res.num_visited += dfa_visited;
-            } else if (st == ST_I) {  // gap_affine.rs:307-322
-                if (relax(it.node, it.offset, ST_M, score)) {
-                    push(it.node, nb.dist_min, nb.dist_max, it.offset, ST_M, score);
-                    ++res.num_queued;
-                }
-                if (it.offset < Q && relax(it.node, it.offset + 1, ST_I, add(score, p.e))) {
-                    push(it.node, nb.dist_min, nb.dist_max, it.offset + 1, ST_I, add(score, p.e));
-                    ++res.num_queued;
-                }
-            } else {  // gap_affine.rs:323-341
-                if (relax(it.node, it.offset, ST_M, score)) {
-                    push(it.node, nb.dist_min, nb.dist_max, it.offset, ST_M, score);
-                    ++res.num_queued;
-                }
-                const uint32_t se = na.succ_off + n_succ;
-                for (uint32_t k = na.succ_off; k < se; ++k) {
-                    const uint32_t c = g.succ[k];
-                    CellT *cc = cell(c, it.offset, ST_D);
+                // ---- the one place where states are relaxed and queued ----
+                for (uint32_t ti = 0;; ++ti) {
+                    uint32_t n_, o_, s_, v_, qv_;
+                    if (ti < nt) {
+                        n_ = ti == 0 ? tn0 : (ti == 1 ? tn1 : tn2);
+                        o_ = ti == 0 ? to0 : (ti == 1 ? to1 : to2);
+                        s_ = ti == 0 ? ts0 : (ti == 1 ? ts1 : ts2);
+                        v_ = ti == 0 ? tv0 : (ti == 1 ? tv1 : tv2);
+                        qv_ = ((open_mask >> ti) & 1) ? open_queued : v_;
+                    } else if (dk < dk_end) {
+                        n_ = g.succ[dk++], o_ = it.offset, s_ = ST_D, v_ = qv_ = add(score, p.e);
+                    } else {
+                        break;
+                    }
+                    CellT *cc = cell(n_, o_, s_);
                     const CellT ccur = *cc;
-                    const NodeB cb = node_b(c);  // loaded with the cell, used only when the relaxation succeeds
-                    if (relax_loaded(cc, ccur, add(score, p.e))) {
-                        push(c, cb.dist_min, cb.dist_max, it.offset, ST_D, add(score, p.e));
+                    const NodeB b = node_b(n_);  // loaded with the cell, used only when the relaxation succeeds
+                    if (relax_loaded(cc, ccur, v_)) {
+                        push(n_, b.dist_min, b.dist_max, o_, s_, qv_);
                         ++res.num_queued;
                     }
                 }
             }
+            if (st == ST_M && !done) res.num_visited += dfa_visited;
         }
         res.score = end_score;
         if (err != RP_OK) {

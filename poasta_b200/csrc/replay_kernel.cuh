@@ -37,7 +37,7 @@ constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few worke
 
 // MINB = minimum resident CTAs per SM the register allocation must allow. Only lane 0 of a warp runs the state machine
 // but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
-template <typename CellT, int MINB>
+template <typename CellT, int MINB, int HEUR>
 __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
     __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];  // queue-head window of each worker
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
 #if defined(RP_PROFILE)
             const long long t_begin = clock64();
 #endif
-            replay::Search<CellT> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
+            replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;
