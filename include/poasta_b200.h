@@ -89,6 +89,10 @@ int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *c
 int poasta_last_batch_search_ms(double *search_ms);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* Measured integer issue peaks of `device` in 10^12 lane-operations per second: 32-bit add, xor+min pairs (2 operations),
+ * and the fused add+min the DP fill uses (DPX, counted as 2 operations). The DP fill's roofline is stated
+ * against these; no reference counterpart. */
+int poasta_measure_int_peak(int device, double *add_tops, double *min_tops, double *addmin_tops);
 
 /* ---- POAGraph (graphs/poa.rs) -------------------------------------------------------------- */
 typedef struct poasta_graph poasta_graph; /* opaque POAGraph<u32> */

@@ -127,6 +127,14 @@ def last_batch_io():
     return a.value, b.value
 
 
+def measure_int_peak(device=0):
+    """Measured integer issue peaks of the device in Tera lane-operations/s: (add, xor+min, fused add+min)."""
+    lib = _lib.load()
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    check(lib.poasta_measure_int_peak(device, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
 class PoastaAligner:
     def __init__(self, config=AffineMinGapCost(), aln_type=AlignmentType.Global, device=0, tiebreak=TIEBREAK_EXACT):
         self.config, self.aln_type, self.device, self.tiebreak = config, aln_type, device, tiebreak

@@ -43,6 +43,7 @@ struct BatchDev {
     const AlnDesc *alns;
     const uint8_t *node_sym;
     const uint32_t *node_info, *node_id, *ord_slot, *pred_off, *pred_rank, *pred_slot;
+    const RowRec *rows;
     const uint8_t *queries;
     uint32_t n_alns;
     int x, oe, e;
@@ -417,7 +418,7 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sms = 0;
-    Buf graphs, alns, node_sym, node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
+    Buf rows, graphs, alns, node_sym, node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
     Buf r_graphs, r_nodes, r_succ, r_pred, r_bub, r_path_off, r_path_rem, r_slabs, r_stats;
@@ -507,6 +508,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
               c.node_id.reserve(pb.node_id.size() * 4) && c.ord_slot.reserve(pb.ord_slot.size() * 4) &&
+              c.rows.reserve(pb.rows.size() * sizeof(RowRec)) &&
               c.pred_off.reserve(pb.pred_off.size() * 4) &&
               c.pred_rank.reserve(pb.pred_rank.size() * 4 + 4) && c.pred_slot.reserve(pb.pred_slot.size() * 4 + 4) &&
               c.queries.reserve(pb.queries.size() + 4) &&
@@ -521,6 +523,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaMemcpyAsync(c.node_info.d, pb.node_info.data(), pb.node_info.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.node_id.d, pb.node_id.data(), pb.node_id.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.ord_slot.d, pb.ord_slot.data(), pb.ord_slot.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c.rows.d, pb.rows.data(), pb.rows.size() * sizeof(RowRec), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c.pred_off.d, pb.pred_off.data(), pb.pred_off.size() * 4, cudaMemcpyHostToDevice, s));
     if (!pb.pred_rank.empty()) {
         CK(cudaMemcpyAsync(c.pred_rank.d, pb.pred_rank.data(), pb.pred_rank.size() * 4, cudaMemcpyHostToDevice, s));
@@ -530,7 +533,8 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaMemsetAsync(c.counter.d, 0, 4, s));
     CK(cudaMemsetAsync(c.scores.d, 0x3F, n * 4, s));
     tl_h2d += pb.graphs.size() * sizeof(GraphDesc) + n * sizeof(AlnDesc) + pb.node_sym.size() + pb.node_info.size() * 4 +
-              pb.node_id.size() * 4 + pb.pred_off.size() * 4 + pb.pred_rank.size() * 4 + pb.queries.size();
+              pb.node_id.size() * 4 + pb.pred_off.size() * 4 + pb.pred_rank.size() * 8 + pb.ord_slot.size() * 4 +
+              pb.rows.size() * sizeof(RowRec) + pb.queries.size();
 
     BatchDev P;
     P.graphs = (const GraphDesc *)c.graphs.d;
@@ -539,6 +543,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.node_info = (const uint32_t *)c.node_info.d;
     P.node_id = (const uint32_t *)c.node_id.d;
     P.ord_slot = (const uint32_t *)c.ord_slot.d;
+    P.rows = (const RowRec *)c.rows.d;
     P.pred_off = (const uint32_t *)c.pred_off.d;
     P.pred_rank = (const uint32_t *)c.pred_rank.d;
     P.pred_slot = (const uint32_t *)c.pred_slot.d;
@@ -976,6 +981,31 @@ static int align_problems(int device, const std::vector<Problem> &probs, const p
 
 using namespace poasta;
 
+// ---- integer issue peak of this device (the DP fill is bound by integer issue, and that peak is not in
+// MEASURED_PEAKS.json). Each thread runs 8 independent dependent-chains so the pipes stay full; ops = lane-operations.
+template <int MODE>  // 0: add, 1: min, 2: fused add+min (DPX __viaddmin_s32, counted as 2 operations)
+__global__ void __launch_bounds__(256) int_peak_kernel(int *out, int iters, int seed) {
+    int a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * 8 + k;
+    const int b = seed | 1, c = seed + 12345;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 0) a[k] = a[k] + a[(k + 1) & 7];  // cross-chain adds cannot be folded into a multiply
+                else if (MODE == 1) a[k] = min(a[k] ^ u, c + k);  // the xor keeps the compiler from collapsing the chain
+                else a[k] = __viaddmin_s32(a[k], b, c + u);
+            }
+        }
+    }
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    if (r == 0x7FFFFFFF) out[blockIdx.x * blockDim.x + threadIdx.x] = r;  // practically never: keeps the work live
+}
+
 extern "C" {
 
 int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_graphs, const uint8_t *const *queries,
@@ -1022,6 +1052,44 @@ int poasta_last_batch_search_ms(double *search_ms) {
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = tl_h2d;
     if (d2h_bytes) *d2h_bytes = tl_d2h;
+    return 0;
+}
+
+int poasta_measure_int_peak(int device, double *add_tops, double *min_tops, double *addmin_tops) {
+    DeviceContext &c = ctx_for(device);
+    int rc = c.init(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(c.device));
+    int *out = nullptr;
+    const int blocks = c.n_sms * 8, iters = 64;
+    CK(cudaMalloc(&out, (size_t)blocks * 256 * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double tops[3] = {0, 0, 0};
+    for (int mode = 0; mode < 3; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+            CK(cudaEventRecord(e0, c.stream));
+            if (mode == 0) int_peak_kernel<0><<<blocks, 256, 0, c.stream>>>(out, iters, rep + 3);
+            else if (mode == 1) int_peak_kernel<1><<<blocks, 256, 0, c.stream>>>(out, iters, rep + 3);
+            else int_peak_kernel<2><<<blocks, 256, 0, c.stream>>>(out, iters, rep + 3);
+            CK(cudaEventRecord(e1, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) best = std::min(best, ms);
+        }
+        // mode 1 issues two instructions (xor, min) per step and counts one operation each; mode 2 counts add and min
+        const double ops = (double)blocks * 256 * iters * 16 * 8 * (mode == 0 ? 1 : 2);
+        tops[mode] = ops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (add_tops) *add_tops = tops[0];
+    if (min_tops) *min_tops = tops[1];
+    if (addmin_tops) *addmin_tops = tops[2];
     return 0;
 }
 

@@ -28,6 +28,7 @@ struct GraphDesc {
     uint32_t max_in_degree;
     uint32_t n_stored;      // rows that later rows read from the row store (warp kernel)
     uint32_t n_ord_rows;    // rows with >= 2 predecessors: they own a block of predecessor ordinals in the warp kernel's trace
+    uint32_t pred_base;     // first entry of this graph in pred_rank / pred_slot
 };
 
 struct AlnDesc {
@@ -48,11 +49,23 @@ constexpr uint32_t INFO_IS_START = 1u << 11;
 constexpr uint32_t INFO_STORE = 1u << 12;  // some later row reads this row from the row store (warp kernel)
 constexpr uint32_t INFO_SLOT_SHIFT = 13;   // bits 13.. : index of the row inside the compact row store
 
+// Everything the warp kernel needs to start a row, in one 128-bit load per row (fetched one row ahead):
+//   x  node_info of the row
+//   y  first index of the row's predecessors in pred_rank / pred_slot (relative to the graph)
+//   z  in-degree | node symbol << 24
+//   w  for rows with exactly one predecessor: ROW_PREV_IN_REGS when that predecessor is the row just before (the common
+//      case: nothing is read from memory), else its slot in the row store; unused otherwise
+struct alignas(16) RowRec {
+    uint32_t info, pred_begin, npred_sym, pred0_slot;
+};
+constexpr uint32_t ROW_PREV_IN_REGS = 0xFFFFFFFFu;
+
 // One graph in the kernels' rank-ordered layout (see the header comment); pred_off is relative to this graph's pred_rank.
 struct PackedGraph {
     uint32_t V = 0, max_in_degree = 0, n_stored = 0, n_ord_rows = 0;
     std::vector<uint8_t> node_sym;
     std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
+    std::vector<RowRec> rows;
 
     void build(const poasta_graph_view &g, std::vector<uint32_t> &rank_scratch) {
         V = g.n_nodes;
@@ -102,6 +115,15 @@ struct PackedGraph {
             const uint32_t pi = node_info[pred_rank[k]];
             pred_slot[k] = (pi & INFO_STORE) ? (pi >> INFO_SLOT_SHIFT) : 0xFFFFFFFFu;
         }
+        rows.resize(V);
+        for (uint32_t r = 0; r < V; ++r) {
+            const uint32_t np = pred_off[r + 1] - pred_off[r];
+            RowRec &rr = rows[r];
+            rr.info = node_info[r];
+            rr.pred_begin = pred_off[r];
+            rr.npred_sym = np | ((uint32_t)node_sym[r] << 24);
+            rr.pred0_slot = np == 1 ? (pred_rank[pred_off[r]] + 1 == r ? ROW_PREV_IN_REGS : pred_slot[pred_off[r]]) : 0;
+        }
     }
 };
 
@@ -110,6 +132,7 @@ struct PackedBatch {
     std::vector<AlnDesc> alns;
     std::vector<uint8_t> node_sym;
     std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
+    std::vector<RowRec> rows;  // pred_begin is relative to the graph's first predecessor entry (GraphDesc::pred_base)
     std::vector<uint8_t> queries;
     uint64_t trace_elems = 0;
     uint64_t ptrace_words = 0;
@@ -130,6 +153,7 @@ struct PackedBatch {
         pred_off.clear();
         pred_rank.clear();
         pred_slot.clear();
+        rows.clear();
         queries.clear();
         trace_elems = ptrace_words = out_elems = max_cells = total_cells = max_store_cells = 0;
         max_in_degree = 0;
@@ -152,6 +176,8 @@ struct PackedBatch {
         gd.max_in_degree = pg.max_in_degree;
         gd.n_stored = pg.n_stored;
         gd.n_ord_rows = pg.n_ord_rows;
+        gd.pred_base = (uint32_t)pred_rank.size();
+        rows.insert(rows.end(), pg.rows.begin(), pg.rows.end());
         node_sym.insert(node_sym.end(), pg.node_sym.begin(), pg.node_sym.end());
         node_info.insert(node_info.end(), pg.node_info.begin(), pg.node_info.end());
         node_id.insert(node_id.end(), pg.node_id.begin(), pg.node_id.end());

@@ -17,6 +17,9 @@
 // score-equality backtrace (gap_affine.rs:550-657), as in dp_fill_kernel.
 // Rows with several predecessors, or whose predecessor is not the previous row, read predecessor rows from a
 // per-warp row store in HBM; only rows that some later row needs from there are written to it (host flag).
+// Every row starts from ONE 128-bit record (RowRec) fetched a row ahead, so a plain row issues no dependent loads at all.
+// Measured and rejected: prefetch.global.L1 of the predecessor rows the next row will read (predecessors are a median of
+// 2 rows back, i.e. already cache-resident) made the fill 5 % slower (profiles/README.md).
 #pragma once
 
 namespace poasta {
@@ -64,10 +67,9 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
         const GraphDesc gd = P.graphs[ad.graph];
         const int Q = (int)ad.Q, W = (int)ad.W, V = (int)gd.V;
         const uint8_t *q = P.queries + ad.query_base;
-        const uint8_t *sym = P.node_sym + gd.node_base;
-        const uint32_t *info = P.node_info + gd.node_base;
+        const RowRec *rows = P.rows + gd.node_base;
         const uint32_t *ord_slot = P.ord_slot + gd.node_base;
-        const uint32_t *poff = P.pred_off + gd.predoff_base;
+        const uint32_t *prank = P.pred_rank + gd.pred_base, *pslot = P.pred_slot + gd.pred_base;
         uint32_t *planes = (uint32_t *)P.trace + ad.ptrace_base;           // V * 32 lanes * PL_WORDS words
         uint32_t *ord_store = planes + (uint64_t)V * 32 * PL_WORDS;         // n_ord_rows * 1024 words, [c][lane] per row
 
@@ -94,12 +96,15 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
 #pragma unroll
         for (int c = 0; c < C; ++c) Mp[c] = WINF, Dp[c] = WINF;
 
+        RowRec next_row = rows[0];
         for (int r = 0; r < V; ++r) {
-            const uint32_t inf = info[r];
-            const int vs = sym[r];
+            const RowRec row = next_row;
+            if (r + 1 < V) next_row = rows[r + 1];  // in flight while this row is computed
+            const uint32_t inf = row.info;
+            const int vs = (int)(row.npred_sym >> 24);
             const bool is_end = inf & INFO_IS_END, is_start = inf & INFO_IS_START;
-            const uint32_t pb = poff[r], pe = poff[r + 1];
-            const int npred = (int)(pe - pb);
+            const int npred = (int)(row.npred_sym & 0xFFFFFFu);
+            const uint32_t pb = row.pred_begin, pe = pb + (uint32_t)npred;
             const SymMask ms = mask_of(vs);
             const uint32_t openD_mask = is_end ? 0u : (valid & ~ms.n);
             uint32_t openI_mask = 0;
@@ -112,9 +117,9 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
 
             if (npred == 1 && !is_end) {
                 // ---- single predecessor: registers (pred == r-1) or one reload from the row store ----
-                const int p = (int)P.pred_rank[pb];
-                if (p != r - 1) {
-                    const int *Ms = slot + (uint64_t)(2 * P.pred_slot[pb]) * W;
+                const bool reload = row.pred0_slot != ROW_PREV_IN_REGS;
+                if (reload) {
+                    const int *Ms = slot + (uint64_t)(2 * row.pred0_slot) * W;
                     if (lane_active) {
 #pragma unroll
                         for (int k = 0; k < C / 4; ++k) {
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
                     }
                 }
                 int prevM = prev_left;
-                if (p != r - 1) {  // reloaded row: fetch the left neighbour's last column again
+                if (reload) {  // reloaded row: fetch the left neighbour's last column again
                     prevM = __shfl_up_sync(0xFFFFFFFFu, Mp[C - 1], 1);
                     if (lane == 0) prevM = WINF;
                 }
@@ -153,20 +158,21 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
 #pragma unroll
                 for (int cc = 0; cc < C / 8; ++cc) {
                     int Xa[8], dom[8], dem[8];
+                    int dop01[2][8];   // the "open" candidates of the first two predecessors (see the equality test below)
                     uint32_t ords[8];  // mord | dopen_ord << 10 | dext_ord << 20
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) Xa[c] = WINF, dom[c] = WINF, dem[c] = WINF, ords[c] = 0;
+                    for (int c = 0; c < 8; ++c) Xa[c] = WINF, dom[c] = WINF, dem[c] = WINF, ords[c] = 0, dop01[0][c] = dop01[1][c] = WINF;
                     const int jb = j0 + cc * 8;
                     if (jb < W) {
                         for (uint32_t k = pb; k < pe; ++k) {
                             const uint32_t ord = k - pb;
                             int mp[9], dp[8];
-                            if ((int)P.pred_rank[k] == r - 1) {  // the row just computed is still in registers
+                            if ((int)prank[k] == r - 1) {  // the row just computed is still in registers
                                 mp[0] = cc == 0 ? prev_left : Mp[cc * 8 - (cc == 0 ? 0 : 1)];
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) mp[c + 1] = Mp[cc * 8 + c], dp[c] = Dp[cc * 8 + c];
                             } else {
-                                const int *Ms = slot + (uint64_t)(2 * P.pred_slot[k]) * W;
+                                const int *Ms = slot + (uint64_t)(2 * pslot[k]) * W;
                                 const int4 ma = *reinterpret_cast<const int4 *>(Ms + jb), mb = *reinterpret_cast<const int4 *>(Ms + jb + 4);
                                 const int4 da = *reinterpret_cast<const int4 *>(Ms + W + jb), db = *reinterpret_cast<const int4 *>(Ms + W + jb + 4);
                                 mp[0] = jb > 0 ? Ms[jb - 1] : WINF;
@@ -179,6 +185,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
                                 const int cand = is_end ? mp[c + 1] : mp[c] + (((ms.m >> cg) & 1) ? 0 : x);
                                 if (cand < Xa[c]) Xa[c] = cand, ords[c] = (ords[c] & ~0x3FFu) | ord;
                                 const int dop = mp[c + 1] + oe, dex = dp[c] + e;
+                                if (WRITE_TRACE && ord == 0) dop01[0][c] = dop;
+                                if (WRITE_TRACE && ord == 1) dop01[1][c] = dop;
                                 if (dop < dom[c]) dom[c] = dop, ords[c] = (ords[c] & ~(0x3FFu << 10)) | (ord << 10);
                                 if (dex < dem[c]) dem[c] = dex, ords[c] = (ords[c] & ~(0x3FFu << 20)) | (ord << 20);
                             }
@@ -193,10 +201,18 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, 3) dp_fill_warp_kernel
                         if (is_start && j == 0) xd = 0;
                         bool is_open = dom[c] == d;
                         if (WRITE_TRACE && d < WFIN && !is_open && !((openD_mask >> cg) & 1) && npred > 1 && dom[c] < d && j <= Q) {
-                            // rare: a non-minimal "open" candidate equals D although opening is not allowed here
-                            // (the reference's backtrace tests score equality only)
-                            for (uint32_t k = pb; k < pe; ++k) {
-                                const int mpj = (int)P.pred_rank[k] == r - 1 ? Mp[cg] : slot[(uint64_t)(2 * P.pred_slot[k]) * W + j];
+                            // a non-minimal "open" candidate equals D although opening is not allowed here (the reference's
+                            // backtrace tests score equality only; first predecessor in order wins). About one column in eight
+                            // of a merge row gets here, so the first two candidates are kept in registers.
+                            if (dop01[0][c] == d) {
+                                is_open = true;
+                                ords[c] = ords[c] & ~(0x3FFu << 10);
+                            } else if (dop01[1][c] == d) {
+                                is_open = true;
+                                ords[c] = (ords[c] & ~(0x3FFu << 10)) | (1u << 10);
+                            } else
+                            for (uint32_t k = pb + 2; k < pe; ++k) {
+                                const int mpj = (int)prank[k] == r - 1 ? Mp[cg] : slot[(uint64_t)(2 * pslot[k]) * W + j];
                                 if (mpj + oe == d) {
                                     is_open = true;
                                     ords[c] = (ords[c] & ~(0x3FFu << 10)) | ((k - pb) << 10);
