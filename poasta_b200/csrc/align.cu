@@ -417,6 +417,7 @@ struct DeviceContext {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_done = nullptr;  // blocking-sync event: a waiting lane thread sleeps instead of spinning
     int n_sms = 0;
     Buf rows, graphs, alns, node_sym, node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot, queries, scratch, trace, scores, counter, out_r, out_q,
         n_pairs, status, offsets, dense_r, dense_q;
@@ -442,6 +443,7 @@ struct DeviceContext {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return POASTA_ERR_CUDA;
         cudaEventCreate(&ev0);
         cudaEventCreate(&ev1);
+        cudaEventCreateWithFlags(&ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
         device = dev;
         return 0;
     }
@@ -449,7 +451,7 @@ struct DeviceContext {
 
 // One context per (device, pipeline lane): a lane is one host thread + one stream driving its share of a batch, so that
 // the host work of one lane (flattening, packing, graph insertion) overlaps the kernels of the others.
-constexpr int MAX_LANES = 8;
+constexpr int MAX_LANES = 32;
 static thread_local int tl_lane = 0;        // pipeline lane of the calling thread
 static thread_local int tl_lane_count = 1;  // lanes sharing the device right now (memory budgets are divided by it)
 static DeviceContext &ctx_for(int device) {
@@ -478,6 +480,14 @@ struct ChunkResult {
     std::vector<int32_t> status;
     const uint32_t *dense_r = nullptr, *dense_q = nullptr;  // pinned, valid until the next run_chunk on this context
 };
+
+// Waits for everything queued on the lane's stream. Kernels of the search path run for seconds: the lane thread sleeps on a
+// blocking-sync event so its core is free for the host phases of the other lanes.
+static cudaError_t wait_stream(DeviceContext &c) {
+    cudaError_t e = cudaEventRecord(c.ev_done, c.stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c.ev_done);
+}
 
 // Runs one packed batch (must fit the memory budget) and leaves results in pinned host memory.
 static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_params &prm, ChunkResult &res, bool scores_only) {
@@ -576,7 +586,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         CK(cudaGetLastError());
         if (!c.h_scores.reserve(n * 4)) return POASTA_ERR_CUDA;
         CK(cudaMemcpyAsync(c.h_scores.h, c.scores.d, n * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(wait_stream(c));
         float ms0 = 0;
         cudaEventElapsedTime(&ms0, c.ev0, c.ev1);
         tl_kernel_ms += ms0;
@@ -606,7 +616,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     CK(cudaMemcpyAsync(c.h_scores.h, c.scores.d, n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_npairs.h, c.n_pairs.d, n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_status.h, c.status.d, n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(c));
     const uint32_t total_pairs = ((uint32_t *)c.h_offsets.h)[n];
     if (!c.dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.dense_q.reserve((size_t)total_pairs * 4 + 4) ||
         !c.h_dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.h_dense_q.reserve((size_t)total_pairs * 4 + 4))
@@ -618,7 +628,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         CK(cudaMemcpyAsync(c.h_dense_r.h, c.dense_r.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(c.h_dense_q.h, c.dense_q.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(c));
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev0, c.ev1);
     tl_kernel_ms += ms;
@@ -833,7 +843,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     CK(cudaMemcpyAsync(c.h_npairs.h, c.n_pairs.d, n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_status.h, c.status.d, n * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_stats.h, c.r_stats.d, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(c));
     const uint32_t total_pairs = ((uint32_t *)c.h_offsets.h)[n];
     if (!c.dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.dense_q.reserve((size_t)total_pairs * 4 + 4) ||
         !c.h_dense_r.reserve((size_t)total_pairs * 4 + 4) || !c.h_dense_q.reserve((size_t)total_pairs * 4 + 4))
@@ -845,7 +855,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         CK(cudaMemcpyAsync(c.h_dense_r.h, c.dense_r.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(c.h_dense_q.h, c.dense_q.d, (size_t)total_pairs * 4, cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(c));
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev0, c.ev1);
     tl_search_ms += ms;
@@ -1225,7 +1235,7 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
     if (const char *e = getenv("POASTA_LANES")) lanes = std::max(1, std::min(MAX_LANES, atoi(e)));
     else lanes = (int)std::max<uint32_t>(1, std::min<uint32_t>(4, n_families / 256));
     // host phases of different lanes rarely coincide (the others wait on their kernels), so lanes share the cores generously
-    unsigned threads_per_lane = std::max(1u, std::min(64u, hw) / lanes);
+    unsigned threads_per_lane = std::max(2u, std::min(64u, hw) / lanes);
     if (const char *e = getenv("POASTA_THREADS_PER_LANE")) threads_per_lane = std::max(1, atoi(e));
     struct LaneOut {
         int rc = 0;
