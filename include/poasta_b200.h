@@ -87,6 +87,10 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
 int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *cells);
 /* Milliseconds the order-exact search kernel took in the last call on this thread (0 with tiebreak = 1). */
 int poasta_last_batch_search_ms(double *search_ms);
+/* Device time of the last call on this thread: kernels only, CUDA events on the launching streams. For poasta_msa_batch*
+ * the pipeline lanes run their kernels concurrently, so this is the LARGEST per-lane sum (the device-side critical path
+ * of the call), whereas poasta_last_batch_stats / _search_ms report the sums over all lanes. */
+int poasta_last_batch_device_ms(double *device_ms);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Measured integer issue peaks of `device` in 10^12 lane-operations per second: 32-bit add, xor+min pairs (2 operations),

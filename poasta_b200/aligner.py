@@ -120,6 +120,14 @@ def last_batch_search_ms():
     return ms.value
 
 
+def last_batch_device_ms():
+    """Device-side critical path of the last call: the largest per-lane sum of kernel time (lanes overlap on the device)."""
+    lib = _lib.load()
+    ms = C.c_double()
+    lib.poasta_last_batch_device_ms(C.byref(ms))
+    return ms.value
+
+
 def last_batch_io():
     lib = _lib.load()
     a, b = C.c_uint64(), C.c_uint64()

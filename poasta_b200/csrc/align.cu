@@ -462,6 +462,7 @@ static DeviceContext &ctx_for(int device) {
 }
 
 static thread_local double tl_kernel_ms = 0, tl_search_ms = 0;
+static thread_local double tl_lane_max_ms = -1;  // msa batches: the largest per-lane sum of kernel time (lanes overlap on the device)
 static thread_local uint32_t tl_launches = 0;
 static thread_local uint64_t tl_cells = 0;
 static thread_local uint64_t tl_h2d = 0, tl_d2h = 0;
@@ -1023,6 +1024,7 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
                        poasta_result *results) {
     if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
     tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_lane_max_ms = -1;
     std::vector<Problem> probs(n_queries);
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
@@ -1056,6 +1058,11 @@ int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *c
 
 int poasta_last_batch_search_ms(double *search_ms) {
     if (search_ms) *search_ms = tl_search_ms;
+    return 0;
+}
+
+int poasta_last_batch_device_ms(double *device_ms) {
+    if (device_ms) *device_ms = tl_lane_max_ms >= 0 ? tl_lane_max_ms : tl_kernel_ms + tl_search_ms;
     return 0;
 }
 
@@ -1265,9 +1272,11 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
     uint64_t cells = 0;
     int rc = 0;
     tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_lane_max_ms = 0;
     for (const LaneOut &o : outs) {
         if (o.rc && !rc) rc = o.rc;
         cells += o.cells;
+        tl_lane_max_ms = std::max(tl_lane_max_ms, o.kernel_ms + o.search_ms);
         tl_kernel_ms += o.kernel_ms, tl_search_ms += o.search_ms, tl_launches += o.launches, tl_h2d += o.h2d, tl_d2h += o.d2h;
     }
     tl_cells = cells;

@@ -199,3 +199,17 @@ def test_query_longer_than_warp_kernel_limit():
     assert rc == 0 and list(scores[0]) == list(osc) and graphs[0].to_fasta() == expect
     for g, seq, sc, pairs in _progressive_cases(fa, max_align=2):
         _check_both_modes(g, seq, sc, pairs)
+
+
+@pytest.mark.gpu
+def test_int_peak_probe_and_device_time():
+    """The integer issue micro-benchmark bench.py reports and the device-time accessor."""
+    from poasta_b200 import aligner
+    add_t, min_t, addmin_t = aligner.measure_int_peak(0)
+    for v in (add_t, min_t, addmin_t):
+        assert 1.0 < v < 200.0, (add_t, min_t, addmin_t)  # Tera lane-operations per second on any B200
+    fams = [synth.config2_family(f, n_seqs=3, root_len=120, rate=0.05) for f in range(4)]
+    msa_batch(fams, device=0)
+    crit = aligner.last_batch_device_ms()
+    kms, launches, cells = aligner.last_batch_stats()
+    assert 0.0 < crit <= kms + aligner.last_batch_search_ms() + 1e-6
