@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include "../poasta_b200/csrc/flatten.hpp"
@@ -15,6 +16,7 @@
 #include "dp_model.hpp"
 #include "../poasta_b200/csrc/replay_core.hpp"
 #include "../poasta_b200/csrc/search_index.hpp"
+#include "../poasta_b200/csrc/device_batch.hpp"
 
 using namespace oracle;
 
@@ -342,6 +344,32 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     }
     if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = used_blocks, stats[4] = used_items;
     return r.status;
+}
+
+// The product's host-side packing of one graph for the DP kernels (device_batch.hpp) and its node records for the search
+// kernel (search_index.hpp), dumped so CPU tests can pin the layouts the device code reads. TEST HOOK ONLY.
+//   meta[4] = V, max_in_degree, n_stored, n_ord_rows; rows = 4 words per row (RowRec); recs = 8 words per node (NodeRec)
+int packed_graph_dump(const poasta_graph_view *view, uint32_t *meta, uint32_t *rows, uint32_t *node_info, uint32_t *node_id,
+                      uint32_t *ord_slot, uint32_t *pred_off, uint32_t *pred_rank, uint32_t *pred_slot, uint8_t *node_sym, uint32_t *recs) {
+    poasta::PackedGraph pg;
+    std::vector<uint32_t> scratch;
+    pg.build(*view, scratch);
+    meta[0] = pg.V, meta[1] = pg.max_in_degree, meta[2] = pg.n_stored, meta[3] = pg.n_ord_rows;
+    static_assert(sizeof(poasta::RowRec) == 16 && sizeof(poasta::replay::NodeRec) == 32, "device record sizes");
+    memcpy(rows, pg.rows.data(), pg.rows.size() * sizeof(poasta::RowRec));
+    memcpy(node_info, pg.node_info.data(), pg.node_info.size() * 4);
+    memcpy(node_id, pg.node_id.data(), pg.node_id.size() * 4);
+    memcpy(ord_slot, pg.ord_slot.data(), pg.ord_slot.size() * 4);
+    memcpy(pred_off, pg.pred_off.data(), pg.pred_off.size() * 4);
+    memcpy(pred_rank, pg.pred_rank.data(), pg.pred_rank.size() * 4);
+    memcpy(pred_slot, pg.pred_slot.data(), pg.pred_slot.size() * 4);
+    memcpy(node_sym, pg.node_sym.data(), pg.node_sym.size());
+    poasta::SearchIndex si;
+    si.build(*view, false);
+    std::vector<poasta::replay::NodeRec> nr;
+    si.node_records(*view, nr);
+    memcpy(recs, nr.data(), nr.size() * sizeof(poasta::replay::NodeRec));
+    return 0;
 }
 
 // event counters of the host build of the search core (tools/search_stats.py); reading resets them
