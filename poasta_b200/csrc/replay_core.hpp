@@ -58,12 +58,15 @@
 #if defined(RP_COUNT) && !defined(__CUDA_ARCH__)
 namespace poasta { namespace replay {
 enum { C_POP_M, C_POP_D, C_POP_I, C_POP_STALE, C_DFA_STEP, C_DFA_MATCH, C_DFA_MISMATCH, C_DFA_RELAX_FAIL, C_PRUNE_CALL, C_PRUNE_BUB,
-       C_PRUNE_NOREACH, C_PRUNE_PROBE, C_PRUNE_SCORE, C_PUSH, C_RELAX, C_RELAX_OK, C_WINDOW_MOVE, C_POP_SCAN, C_N };
+       C_PRUNE_NOREACH, C_PRUNE_PROBE, C_PRUNE_SCORE, C_PUSH, C_RELAX, C_RELAX_OK, C_WINDOW_MOVE, C_POP_SCAN,
+       C_NEXT_SAME_STACK, C_NEXT_JUST_PUSHED, C_NEXT_OTHER, C_N };
 inline uint64_t rp_counters[C_N];
 } }
 #define RP_CNT(x) (++::poasta::replay::rp_counters[::poasta::replay::x])
+#define RP_STAT(...) __VA_ARGS__
 #else
 #define RP_CNT(x) ((void)0)
+#define RP_STAT(...)
 #endif
 
 namespace poasta {
@@ -275,6 +278,8 @@ struct Search {
     uint32_t f_cur = 0, f_hi = 0, win_base = 0;
     bool q_empty = true;
     int err = RP_OK;
+    // counting builds: how predictable is the next pop? (the item below the popped one / an item queued since / anything else)
+    RP_STAT(uint32_t stat_below = 0; uint32_t stat_pushes_at_pop = 0; uint32_t stat_pushes = 0;)
 #if defined(RP_PROFILE)
     long long prof_prune = 0, prof_push = 0, prof_pop = 0;
     uint32_t prof_n_prune = 0;
@@ -392,6 +397,7 @@ struct Search {
     RP_HD void push(uint32_t node, uint32_t dist_min, uint32_t dist_max, uint32_t off, uint32_t st, uint32_t score) {
         RP_T0;
         RP_CNT(C_PUSH);
+        RP_STAT(++stat_pushes;)
         const uint32_t f = score + h(node, dist_min, dist_max, off, st);
         if (f >= s.f_max) {
             err = RP_PRIORITY_RANGE;
@@ -429,6 +435,10 @@ struct Search {
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
+                    RP_STAT(if (slot + 1 == stat_below) RP_CNT(C_NEXT_SAME_STACK);
+                            else if (stat_pushes != stat_pushes_at_pop) RP_CNT(C_NEXT_JUST_PUSHED);  // approximation: something was queued since
+                            else RP_CNT(C_NEXT_OTHER);
+                            stat_below = out.next; stat_pushes_at_pop = stat_pushes;)
                     head[k] = out.next;
                     s.free_slots[n_free++] = slot;
                     st = k;
