@@ -30,6 +30,9 @@
 // The same source compiles for the host (tests only) so the logic can be checked without a GPU.
 #pragma once
 #include <cstdint>
+#if defined(RP_COUNT) && !defined(__CUDA_ARCH__)
+#include <vector>
+#endif
 
 #if defined(__CUDACC__)
 #define RP_HD __host__ __device__ __forceinline__
@@ -59,7 +62,8 @@
 namespace poasta { namespace replay {
 enum { C_POP_M, C_POP_D, C_POP_I, C_POP_STALE, C_DFA_STEP, C_DFA_MATCH, C_DFA_MISMATCH, C_DFA_RELAX_FAIL, C_PRUNE_CALL, C_PRUNE_BUB,
        C_PRUNE_NOREACH, C_PRUNE_PROBE, C_PRUNE_SCORE, C_PUSH, C_RELAX, C_RELAX_OK, C_WINDOW_MOVE, C_POP_SCAN,
-       C_NEXT_SAME_STACK, C_NEXT_JUST_PUSHED, C_NEXT_OTHER, C_N };
+       C_NEXT_SAME_STACK, C_NEXT_JUST_PUSHED, C_NEXT_OTHER,
+       C_SPEC_BATCH, C_SPEC_ITEMS, C_SPEC_REUSED, C_SPEC_REUSED_PRUNED, C_SPEC_EPOCH_MISS, C_SPEC_ORDER_MISS, C_SPEC_WRONG, C_N };
 inline uint64_t rp_counters[C_N];
 } }
 #define RP_CNT(x) (++::poasta::replay::rp_counters[::poasta::replay::x])
@@ -280,6 +284,49 @@ struct Search {
     int err = RP_OK;
     // counting builds: how predictable is the next pop? (the item below the popped one / an item queued since / anything else)
     RP_STAT(uint32_t stat_below = 0; uint32_t stat_pushes_at_pop = 0; uint32_t stat_pushes = 0;)
+    // counting builds: MODEL of the bucket-parallel evaluation planned for the device. With spec_K > 0 the
+    // read-only half of a visit (stale test + prune test) is evaluated for the top spec_K items of the stack being popped as
+    // if by spec_K lanes at once; the sequential committer reuses a result only if no reached mark / reached score changed
+    // since (spec_epoch) and the items come off the stack in the predicted order. Checked against a fresh evaluation.
+    RP_STAT(struct Spec { uint32_t slot, node, off, st, score, n_exit, exit[4], epoch[4]; bool pruned; };
+            std::vector<uint32_t> spec_exit_epoch;  // per node: bumped when one of its reached marks / reached scores changes
+            Spec spec[64]; uint32_t spec_n = 0, spec_i = 0, spec_K = 0, spec_f = 0, spec_st = 0; const Spec *cur_spec = nullptr;
+            bool prune_pure(uint32_t score, uint32_t node, uint32_t off, uint32_t st) const {
+                const NodeA a = node_a(node);
+                const uint32_t nb = a.counts >> 16;
+                if (nb == 0) return false;
+                const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
+                return prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score) == 1;
+            }
+            void spec_on_pop(uint32_t slot, uint32_t st, uint32_t f) {
+                cur_spec = nullptr;
+                if (!spec_K) return;
+                if (spec_i < spec_n && spec[spec_i].slot == slot) {
+                    cur_spec = &spec[spec_i++];
+                    return;
+                }
+                // a pop from another stack (e.g. the Match state a popped gap state just closed into) leaves the batch alone:
+                // the committer handles that state on its own and comes back to the batch's stack afterwards
+                if (spec_i < spec_n && (f != spec_f || st != spec_st)) return;
+                if (spec_i < spec_n) RP_CNT(C_SPEC_ORDER_MISS);
+                spec_f = f, spec_st = st;
+                spec_n = spec_i = 0;
+                if (spec_exit_epoch.empty()) spec_exit_epoch.assign(g.V, 0);
+                for (uint32_t sl = slot;;) {  // "lanes" 0..K-1 take the items from the top of this stack downwards
+                    const Item it = s.items[sl];
+                    Spec sp{sl, it.node, it.offset, st, it.score, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, prune_pure(it.score, it.node, it.offset, st)};
+                    const NodeA a = node_a(it.node);
+                    const uint32_t nb = a.counts >> 16;
+                    sp.n_exit = nb;  // more than 4 enclosing bubbles: never reused
+                    for (uint32_t b = 0; b < nb && b < 4; ++b) sp.exit[b] = g.bub[a.bub_off + b].exit, sp.epoch[b] = spec_exit_epoch[sp.exit[b]];
+                    spec[spec_n++] = sp;
+                    if (spec_n >= spec_K || spec_n >= 64 || !it.next) break;
+                    sl = it.next - 1;
+                }
+                RP_CNT(C_SPEC_BATCH);
+                rp_counters[C_SPEC_ITEMS] += spec_n;
+                cur_spec = &spec[spec_i++];
+            })
 #if defined(RP_PROFILE)
     long long prof_prune = 0, prof_push = 0, prof_pop = 0;
     uint32_t prof_n_prune = 0;
@@ -315,6 +362,8 @@ struct Search {
         RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
             RP_CNT(C_RELAX_OK);
+            RP_STAT(if ((cur & FLAG) && !spec_exit_epoch.empty())
+                        ++spec_exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
             *c = (CellT)((CellT)v | (CellT)(cur & FLAG));  // a reached offset stays reached when its score improves
             return true;
         }
@@ -331,6 +380,8 @@ struct Search {
         RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
             RP_CNT(C_RELAX_OK);
+            RP_STAT(if ((cur & FLAG) && !spec_exit_epoch.empty())
+                        ++spec_exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
             *c = (CellT)((CellT)v | (CellT)(cur & FLAG));
             return true;
         }
@@ -435,6 +486,7 @@ struct Search {
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
+                    RP_STAT(spec_on_pop(slot, k, f_cur);)
                     RP_STAT(if (slot + 1 == stat_below) RP_CNT(C_NEXT_SAME_STACK);
                             else if (stat_pushes != stat_pushes_at_pop) RP_CNT(C_NEXT_JUST_PUSHED);  // approximation: something was queued since
                             else RP_CNT(C_NEXT_OTHER);
@@ -456,6 +508,7 @@ struct Search {
     // ---- reached marks (BTreeSet<offset> per exit; gap_affine.rs:767-773) -------------------------------
     RP_HD void mark_reached(uint32_t node, bool is_exit, uint32_t off, uint32_t st) {
         if (st == ST_M && is_exit) {
+            RP_STAT(if (!spec_exit_epoch.empty()) ++spec_exit_epoch[node];)
             *cell(node, off, ST_M) |= FLAG;
             uint32_t *b = s.rb + 2 * (size_t)node;
             if (b[1] == 0) {
@@ -468,6 +521,19 @@ struct Search {
     }
 
     RP_HD bool prune(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
+        RP_STAT(if (cur_spec && cur_spec->node == node && cur_spec->off == off && cur_spec->st == st && cur_spec->score == score) {
+                    const Spec *sp = cur_spec;
+                    cur_spec = nullptr;
+                    bool fresh = sp->n_exit <= 4;
+                    for (uint32_t b = 0; b < sp->n_exit && b < 4; ++b) fresh = fresh && spec_exit_epoch[sp->exit[b]] == sp->epoch[b];
+                    if (fresh) {
+                        RP_CNT(C_SPEC_REUSED);
+                        if (sp->pruned) RP_CNT(C_SPEC_REUSED_PRUNED);
+                        if (prune_pure(score, node, off, st) != sp->pruned) RP_CNT(C_SPEC_WRONG);
+                        return sp->pruned;
+                    }
+                    RP_CNT(C_SPEC_EPOCH_MISS);
+                })
         const uint32_t nb = a.counts >> 16;
         if (nb == 0) return false;
         RP_T0;
