@@ -373,6 +373,45 @@ int packed_graph_dump(const poasta_graph_view *view, uint32_t *meta, uint32_t *r
     return 0;
 }
 
+// The PRODUCT's search index (poasta_b200/csrc/search_index.hpp) in the same shape as oracle_bubble_index, so tests can
+// compare the two restatements entry by entry. TEST HOOK ONLY.
+void product_bubble_index(const poasta_graph_view *view, uint32_t max_per_node, uint32_t *counts, uint32_t *out_maps, uint32_t *dist,
+                          uint8_t *is_exit) {
+    poasta::SearchIndex si;
+    si.build(*view, false);
+    for (uint32_t n = 0; n < view->n_nodes; ++n) {
+        counts[n] = si.bub_off[n + 1] - si.bub_off[n];
+        for (uint32_t k = 0; k < counts[n] && k < max_per_node; ++k) {
+            const uint32_t *q = si.bub.data() + 4 * (size_t)(si.bub_off[n] + k);
+            uint32_t *o = out_maps + 3 * ((size_t)n * max_per_node + k);
+            o[0] = q[0], o[1] = q[1], o[2] = q[2];
+            // the fourth word is derived: min_dist_to_end of the exit used by the prune test (reached.rs:57-58)
+            if (q[3] != (si.dist_min[q[0]] ? si.dist_min[q[0]] - 1 : 0)) counts[n] = 0xFFFFFFFFu;
+        }
+        dist[2 * n] = si.dist_min[n], dist[2 * n + 1] = si.dist_max[n];
+        is_exit[n] = si.is_exit[n];
+    }
+}
+
+// Host cost of the per-round preparation the product does for every graph (search index, DP packing, node records):
+// milliseconds per call, averaged over `reps`. TEST / MEASUREMENT HOOK ONLY.
+int host_prep_timing(const poasta_graph_view *view, int reps, double *ms_index, double *ms_pack, double *ms_recs) {
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    poasta::SearchIndex si;
+    poasta::PackedGraph pg;
+    std::vector<uint32_t> scratch;
+    std::vector<poasta::replay::NodeRec> nr;
+    double t0 = now();
+    for (int i = 0; i < reps; ++i) si.build(*view, false);
+    double t1 = now();
+    for (int i = 0; i < reps; ++i) pg.build(*view, scratch);
+    double t2 = now();
+    for (int i = 0; i < reps; ++i) nr.clear(), si.node_records(*view, nr);
+    double t3 = now();
+    *ms_index = (t1 - t0) / reps, *ms_pack = (t2 - t1) / reps, *ms_recs = (t3 - t2) / reps;
+    return 0;
+}
+
 // event counters of the host build of the search core (tools/search_stats.py); reading resets them
 int replay_host_counters(uint64_t *out, int cap) {
     namespace rp = poasta::replay;

@@ -49,28 +49,52 @@ struct SearchIndex {
         const uint32_t *pe(uint32_t x) const { return v.pred + v.pred_off[x + 1]; }
     };
 
+    // Work buffers kept per host thread: the index of a family's graph is rebuilt every round (config.rs:128), ~10^5 times
+    // per bench step, so build() allocates nothing once the buffers have grown (it was 350 us per 1.4k-node graph with
+    // per-node vectors and copied bubble stacks; profiles/README.md).
+    struct Scratch {
+        std::vector<uint32_t> order, pos, out_parent, out_child, entrance_exit, stack, queue;
+        std::vector<int64_t> opm;
+        std::vector<uint8_t> seen, from_start;
+        std::vector<std::pair<uint32_t, const uint32_t *>> dfs;
+        struct Open {  // one open bubble on the persistent stack carried by the backward BFS: (distance of the exit from end, exit)
+            uint32_t exit_dist, exit, parent;
+        };
+        std::vector<Open> open;
+        std::vector<uint32_t> top_of, dist_of;  // per queued node: its stack top (index into open, NONE = empty) and BFS distance
+        struct Ent {
+            uint32_t node, exit, min_d;
+        };
+        std::vector<Ent> ents;  // bubble memberships in generation order
+        std::vector<uint32_t> chain;
+    };
+
     void build(const poasta_graph_view &view, bool with_paths) {
+        static thread_local Scratch w;
         const G g{view};
         const uint32_t V = view.n_nodes;
+        const uint32_t NONE = 0xFFFFFFFFu;
         // reverse post-order of the DFS from start, children in adjacency order, marked when pushed (graphs/tools.rs:5-37)
-        std::vector<uint32_t> order;
+        std::vector<uint32_t> &order = w.order;
+        order.clear();
         order.reserve(V);
         {
-            std::vector<uint8_t> seen(V, 0);
-            std::vector<std::pair<uint32_t, const uint32_t *>> st;
+            w.seen.assign(V, 0);
+            auto &st = w.dfs;
+            st.clear();
             st.emplace_back(view.start_node, g.sb(view.start_node));
             while (!st.empty()) {
                 auto &top = st.back();
-                uint32_t child = 0xFFFFFFFFu;
+                uint32_t child = NONE;
                 for (const uint32_t *e = g.se(top.first); top.second != e;) {
                     const uint32_t c = *top.second++;
-                    if (!seen[c]) {
+                    if (!w.seen[c]) {
                         child = c;
                         break;
                     }
                 }
-                if (child != 0xFFFFFFFFu) {
-                    seen[child] = 1;
+                if (child != NONE) {
+                    w.seen[child] = 1;
                     st.emplace_back(child, g.sb(child));
                 } else {
                     order.push_back(top.first);
@@ -78,28 +102,40 @@ struct SearchIndex {
                 }
             }
             std::reverse(order.begin(), order.end());
+            w.from_start = w.seen;
+            w.from_start[view.start_node] = 1;
         }
-        std::vector<int64_t> pos(V, 0), out_parent(V, -1), out_child(V, INT64_MAX);
-        for (size_t i = 0; i < order.size(); ++i) pos[order[i]] = (int64_t)i;
+        // positions in that order; nodes the DFS did not reach keep position 0 like the reference's zero-initialised table.
+        // out_parent: smallest predecessor position (NONE = no predecessor, the reference's -1);
+        // out_child: largest successor position (NONE = no successor, the reference's i64::MAX)
+        w.pos.assign(V, 0);
+        w.out_parent.assign(V, NONE);
+        w.out_child.assign(V, NONE);
+        for (size_t i = 0; i < order.size(); ++i) w.pos[order[i]] = (uint32_t)i;
         for (uint32_t n = 0; n < V; ++n) {
             if (g.pb(n) != g.pe(n)) {
-                int64_t mn = INT64_MAX;
-                for (const uint32_t *p = g.pb(n); p != g.pe(n); ++p) mn = std::min(mn, pos[*p]);
-                out_parent[n] = mn;
+                uint32_t mn = NONE;
+                for (const uint32_t *p = g.pb(n); p != g.pe(n); ++p) mn = std::min(mn, w.pos[*p]);
+                w.out_parent[n] = mn;
             }
             if (g.sb(n) != g.se(n)) {
-                int64_t mx = INT64_MIN;
-                for (const uint32_t *s = g.sb(n); s != g.se(n); ++s) mx = std::max(mx, pos[*s]);
-                out_child[n] = mx;
+                uint32_t mx = 0;
+                for (const uint32_t *s = g.sb(n); s != g.se(n); ++s) mx = std::max(mx, w.pos[*s]);
+                w.out_child[n] = mx;
             }
         }
-        // superbubble scan, high rank to low (finder.rs:109-177); later pairs overwrite earlier ones (index.rs:61-64)
-        const uint32_t NONE = 0xFFFFFFFFu;
-        std::vector<uint32_t> entrance_exit(V, NONE);
+        // superbubble scan, high rank to low (finder.rs:109-177); later pairs overwrite earlier ones (index.rs:61-64).
+        // opm holds "outgoing parent minimum" positions as signed values of the reference: -1 (no predecessor) is kept as
+        // int64 so the min() / equality tests below behave like the reference's i64 arithmetic.
+        w.entrance_exit.assign(V, NONE);
         is_exit.assign(V, 0);
         {
-            std::vector<int64_t> opm(V, 0);
-            std::vector<uint32_t> stack;
+            std::vector<int64_t> &opm = w.opm;
+            opm.assign(V, 0);
+            auto parent_of = [&](uint32_t n) -> int64_t { return w.out_parent[n] == NONE ? -1 : (int64_t)w.out_parent[n]; };
+            auto child_of = [&](uint32_t n) -> int64_t { return w.out_child[n] == NONE ? INT64_MAX : (int64_t)w.out_child[n]; };
+            auto &stack = w.stack;
+            stack.clear();
             uint32_t cand = NONE;
             auto pop = [&]() {
                 if (stack.empty()) return NONE;
@@ -109,67 +145,74 @@ struct SearchIndex {
             };
             for (int64_t curr = (int64_t)order.size() - 1; curr >= 0; --curr) {
                 const uint32_t n = order[curr];
-                const int64_t far = out_child[n];
+                const int64_t far = child_of(n);
                 if (far == curr + 1) {
                     if (cand != NONE) stack.push_back(cand);
                     cand = order[curr + 1];
                 } else {
                     while (cand != NONE) {
                         const uint32_t c0 = cand;
-                        if (far <= pos[c0]) break;
+                        if (far <= (int64_t)w.pos[c0]) break;
                         cand = pop();
                         if (cand != NONE) opm[cand] = std::min(opm[c0], opm[cand]);
                     }
                 }
                 if (cand != NONE && (uint64_t)opm[cand] == (uint64_t)curr) {
                     const uint32_t c0 = cand;
-                    entrance_exit[n] = c0;
+                    w.entrance_exit[n] = c0;
                     is_exit[c0] = 1;
                     cand = pop();
                     if (cand != NONE) opm[cand] = std::min(opm[c0], opm[cand]);
                 }
-                opm[n] = out_parent[n];
+                opm[n] = parent_of(n);
                 if (cand != NONE) opm[cand] = std::min(opm[n], opm[cand]);
             }
         }
-        // backward BFS from end carrying the stack of open bubbles (index.rs:73-131)
-        struct Entry {
-            uint32_t exit;
-            uint32_t min_d, max_d;
-        };
-        std::vector<std::vector<Entry>> maps(V);
+        // backward BFS from end carrying the stack of open bubbles (index.rs:73-131). The reference clones a Vec per queued
+        // node; here the stacks share structure: `open` is a pool of (exit distance, exit, parent) and a queued node only
+        // remembers its top. A node's memberships are generated in the reference's order: the bubble popped for it when it
+        // was discovered first, then its own stack from bottom to top when it is dequeued.
         dist_min.assign(V, 0);
         dist_max.assign(V, 0);
+        w.ents.clear();
         {
-            typedef std::vector<std::pair<uint32_t, uint32_t>> BStack;  // (distance of the exit from end, exit)
-            struct Item {
-                uint32_t node, dist;
-                BStack stack;
-            };
-            std::deque<Item> queue;
-            BStack init;
-            if (is_exit[view.end_node]) init.emplace_back(0u, view.end_node);
-            queue.push_back({view.end_node, 0, init});
-            std::vector<uint8_t> seen(V, 0);
-            seen[view.end_node] = 1;
-            while (!queue.empty()) {
-                Item it = std::move(queue.front());
-                queue.pop_front();
-                for (auto &b : it.stack) maps[it.node].push_back({b.second, it.dist - b.first, 0});
-                dist_min[it.node] = it.dist;
-                for (const uint32_t *pp = g.pb(it.node); pp != g.pe(it.node); ++pp) {
+            auto &open = w.open;
+            open.clear();
+            w.top_of.assign(V, NONE);
+            w.dist_of.assign(V, 0);
+            auto &queue = w.queue;
+            queue.clear();
+            if (is_exit[view.end_node]) {
+                open.push_back({0u, view.end_node, NONE});
+                w.top_of[view.end_node] = 0;
+            }
+            queue.push_back(view.end_node);
+            w.seen.assign(V, 0);
+            w.seen[view.end_node] = 1;
+            for (size_t head = 0; head < queue.size(); ++head) {
+                const uint32_t node = queue[head];
+                const uint32_t dist = w.dist_of[node], top = w.top_of[node];
+                w.chain.clear();
+                for (uint32_t o = top; o != NONE; o = open[o].parent) w.chain.push_back(o);
+                for (size_t i = w.chain.size(); i-- > 0;) w.ents.push_back({node, open[w.chain[i]].exit, dist - open[w.chain[i]].exit_dist});
+                dist_min[node] = dist;
+                for (const uint32_t *pp = g.pb(node); pp != g.pe(node); ++pp) {
                     const uint32_t p = *pp;
-                    if (seen[p]) continue;
-                    const uint32_t nd = it.dist + 1;
-                    BStack ns = it.stack;
-                    if (entrance_exit[p] != NONE && !ns.empty()) {
-                        const auto top = ns.back();
-                        ns.pop_back();
-                        maps[p].push_back({top.second, nd - top.first, 0});
+                    if (w.seen[p]) continue;
+                    const uint32_t nd = dist + 1;
+                    uint32_t ns = top;
+                    if (w.entrance_exit[p] != NONE && ns != NONE) {
+                        w.ents.push_back({p, open[ns].exit, nd - open[ns].exit_dist});
+                        ns = open[ns].parent;
                     }
-                    if (is_exit[p]) ns.emplace_back(nd, p);
-                    seen[p] = 1;
-                    queue.push_back({p, nd, std::move(ns)});
+                    if (is_exit[p]) {
+                        open.push_back({nd, p, ns});
+                        ns = (uint32_t)open.size() - 1;
+                    }
+                    w.seen[p] = 1;
+                    w.top_of[p] = ns;
+                    w.dist_of[p] = nd;
+                    queue.push_back(p);
                 }
             }
         }
@@ -178,18 +221,19 @@ struct SearchIndex {
             uint32_t mx = 0;
             for (const uint32_t *s = g.sb(n); s != g.se(n); ++s) mx = std::max(mx, dist_max[*s] + 1);
             dist_max[n] = mx;
-            for (auto &b : maps[n]) b.max_d = mx - dist_max[b.exit];
         }
+        // memberships grouped by node, generation order kept inside a node (stable counting sort)
         bub_off.assign(V + 1, 0);
-        bub.clear();
-        for (uint32_t n = 0; n < V; ++n) {
-            for (auto &b : maps[n]) {
-                bub.push_back(b.exit);
-                bub.push_back(b.min_d);
-                bub.push_back(b.max_d);
-                bub.push_back(dist_min[b.exit] ? dist_min[b.exit] - 1 : 0);  // min_dist_to_end used by the prune test (reached.rs:57-58)
-            }
-            bub_off[n + 1] = (uint32_t)(bub.size() / 4);
+        for (const auto &e : w.ents) ++bub_off[e.node + 1];
+        for (uint32_t n = 0; n < V; ++n) bub_off[n + 1] += bub_off[n];
+        bub.resize(4 * w.ents.size());
+        w.chain.assign(bub_off.begin(), bub_off.end() - 1);  // write cursors
+        for (const auto &e : w.ents) {
+            uint32_t *q = bub.data() + 4 * (size_t)w.chain[e.node]++;
+            q[0] = e.exit;
+            q[1] = e.min_d;
+            q[2] = w.from_start[e.node] ? dist_max[e.node] - dist_max[e.exit] : 0;  // the reference leaves 0 for nodes its DFS never saw
+            q[3] = dist_min[e.exit] ? dist_min[e.exit] - 1 : 0;  // min_dist_to_end used by the prune test (reached.rs:57-58)
         }
         path_off.clear();
         path_rem.clear();

@@ -106,3 +106,27 @@ def test_search_node_records():
             assert (symflags & 0xFF) == cv.symbol[v]
             assert pred_off == cv.pred_off[v] and n_pred == cv.pred_off[v + 1] - cv.pred_off[v]
             assert (dist_min, dist_max) == (dmin[v], dmax[v]), v
+
+
+def test_product_search_index_equals_oracle_bubble_index():
+    """search_index.hpp (product, host side of the search kernel) against the oracle's BubbleIndex: bubble lists per node in
+    the same order, distances to `end`, exit flags derived from the oracle's superbubbles."""
+    n_graphs = 0
+    for g in _graphs():
+        cv = H._cview(g)
+        V, M = cv.n_nodes, 16
+        mk = lambda *shape: np.zeros(shape, np.uint32)  # noqa: E731
+        c1, m1, d1 = mk(V), mk(V, M, 3), mk(V, 2)
+        c2, m2, d2 = mk(V), mk(V, M, 3), mk(V, 2)
+        ex = np.zeros(V, np.uint8)
+        p = lambda a: a.ctypes.data_as(H.u32p)  # noqa: E731
+        H.oracle().oracle_bubble_index(C.byref(cv), 0, M, p(c1), p(m1), p(d1))
+        H.oracle().product_bubble_index(C.byref(cv), M, p(c2), p(m2), p(d2), ex.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert c1.max() <= M
+        assert (c1 == c2).all() and (m1 == m2).all() and (d1 == d2).all()
+        pairs = np.zeros(2 * V, np.uint32)
+        nb = H.oracle().oracle_superbubbles(C.byref(cv), 0, p(pairs), V)
+        exits = {int(pairs[2 * i + 1]) for i in range(nb)}
+        assert {v for v in range(V) if ex[v]} == exits
+        n_graphs += 1
+    assert n_graphs >= 10
