@@ -268,6 +268,50 @@ double oracle_msa_many(const char *const *fasta, const size_t *fasta_len, uint32
     return secs;
 }
 
+// Host cost of graph insertion (add_alignment_with_weights + post_process) and CSR flattening for one family: the MSA is built
+// once with the oracle to obtain the alignments, then the insertions are replayed `reps` times. Microseconds per sequence.
+int host_insert_timing(const char *fasta, size_t fasta_len, int reps, double *us_insert, double *us_flatten) {
+    using namespace poasta;
+    auto recs = parse_fasta(fasta, fasta_len);
+    AlignOptions opt;
+    opt.costs = Costs{4, 6, 2};
+    opt.mode = 0, opt.heuristic = 1;
+    std::vector<std::vector<AlignedPair>> alns(recs.size());
+    {
+        POAGraph g;
+        FlatGraph flat;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const uint8_t *s = (const uint8_t *)recs[i].seq.data();
+            if (!g.is_empty()) {
+                flat.build(g);
+                AstarResult r = astar_align(flat.view(), s, recs[i].seq.size(), opt);
+                if (r.status) return -1;
+                alns[i].resize(r.rpos.size());
+                for (size_t k = 0; k < alns[i].size(); ++k) alns[i][k] = {r.rpos[k], r.qpos[k]};
+            }
+            g.add_alignment_with_weights(recs[i].name, s, recs[i].seq.size(), i != 0, alns[i].data(), alns[i].size());
+        }
+    }
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_ins = 0, t_flat = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        POAGraph g;
+        FlatGraph flat;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const uint8_t *s = (const uint8_t *)recs[i].seq.data();
+            const double t0 = now();
+            g.add_alignment_with_weights(recs[i].name, s, recs[i].seq.size(), i != 0, alns[i].data(), alns[i].size());
+            const double t1 = now();
+            flat.build(g);
+            const double t2 = now();
+            t_ins += t1 - t0, t_flat += t2 - t1;
+        }
+    }
+    *us_insert = t_ins / (reps * (double)recs.size());
+    *us_flatten = t_flat / (reps * (double)recs.size());
+    return 0;
+}
+
 // Dense DP model (dp_model.hpp): global mode. Returns score (0x3FFFFFFF when unreachable).
 uint32_t dpmodel_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, uint32_t *rpos,
                        uint32_t *qpos, uint32_t cap, uint32_t *n_pairs, uint32_t *tables_out) {
