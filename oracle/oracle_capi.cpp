@@ -354,7 +354,8 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     ScratchDims d(view->n_nodes, qlen, x, o, e);
     std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), qwin(rp::QWIN * 3, 0), rb((size_t)view->n_nodes * 2, 0),
         dfa((size_t)(view->n_nodes + 2) * 6, 0);
-    const uint32_t max_items = view->n_nodes * (qlen + 1) / 2 + 65536;
+    // generous arena for the host build: every state can be queued once per successful relaxation
+    const uint32_t max_items = 3 * view->n_nodes * (qlen + 2) + 65536;
     const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
     std::vector<uint8_t> planes((size_t)rp::CELL_SLOTS * plane_elems * (cell16 ? 2 : 4));
     if (cell16) std::fill((uint16_t *)planes.data(), (uint16_t *)planes.data() + rp::CELL_SLOTS * plane_elems, (uint16_t)0x7FFF);
