@@ -670,7 +670,8 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
     if (rc) return rc;
     if (prm.mode != 0) return POASTA_ERR_UNSUPPORTED;  // ends-free is an order property of the reference's search, not a DP optimum
     const uint64_t budget = trace_budget_bytes();
-    PackedBatch pb;
+    // kept per host thread: a lane packs ~75 MB per round, and fresh vectors would be re-grown and page-faulted in every round
+    static thread_local PackedBatch pb;
     std::vector<uint32_t> rank_scratch;
     ChunkResult res;
     size_t i = 0;
@@ -907,7 +908,7 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
         if (probs[i].graph->n_nodes <= 2) outs[i].score = probs[i].qlen * 4u;  // empty-graph shortcut (aligner/mod.rs:124-142)
         else todo.push_back(i);
     }
-    PackedReplay pr;
+    static thread_local PackedReplay pr;  // kept per host thread like the DP batch (~160 MB per round and lane)
     ChunkResult res;
     SearchIndex tmp;
     for (int attempt = 0; attempt < 2 && !todo.empty(); ++attempt) {
