@@ -165,6 +165,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: poasta_b200 has no CPU fallback")
+    # the ranks of one node share its host cores: give every pipeline lane (4 per rank) its share of them
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("POASTA_THREADS_PER_LANE", str(max(1, min(16, (os.cpu_count() or 1) // (local_world * 4)))))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
