@@ -35,7 +35,7 @@ def main():
                                            cell16=cell16, oracle=(a[0], a[1], a[3][:3]), core=(b[0], b[1], b[3][:3])))
                     return 1
             n_aln += 1
-            if a[0] == 0 and mode == 0:
+            if a[0] == 0 and mode == 0 and a[2]:  # Some(empty alignment) is InvalidAlignment in the reference too
                 g.add_alignment_with_weights(name, seq, a[2])
     import ctypes as C
     buf = (C.c_uint64 * 64)()
