@@ -371,7 +371,11 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     uint32_t used_blocks = 0, used_items = 0;
     auto go = [&](auto cell, auto heur) {
         rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
-        if (const char *k = getenv("RP_SPEC_K")) search.spec_K = (uint32_t)atoi(k);  // bucket-parallel evaluation model (counting build)
+        rp::CoopBatch batch{};
+        std::vector<uint32_t> epochs(view->n_nodes, 0);
+        if (const char *k = getenv("RP_SPEC_K")) {  // bucket-parallel evaluation with K lanes (the host runs them as a loop)
+            search.coop = &batch, search.exit_epoch = epochs.data(), search.coop_K = (uint32_t)atoi(k);
+        }
         r = search.run(out_r.data(), out_q.data(), ocap);
         used_items = search.n_items;
     };

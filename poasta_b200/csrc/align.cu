@@ -755,6 +755,10 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     off_reached = off_free + up(max_items * 4);                   // reached bounds: 2 words per node
     off_dfa = off_reached + up((uint64_t)pr.max_V * 8);
     slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);           // DFA frames: 6 words
+#if defined(RP_COOP)
+    const uint64_t off_epoch = slab;                               // per-node epochs of the bucket-parallel evaluation
+    slab += up((uint64_t)pr.max_V * 4);
+#endif
     const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
     const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
@@ -802,6 +806,9 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.slabs = (uint8_t *)c.r_slabs.d;
     B.slab_bytes = slab;
     B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_dfa = off_dfa;
+#if defined(RP_COOP)
+    B.off_epoch = off_epoch;
+#endif
     B.max_items = (uint32_t)max_items;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;

@@ -73,6 +73,16 @@ inline uint64_t rp_counters[C_N];
 #define RP_STAT(...)
 #endif
 
+// Bucket-parallel evaluation: compiled into the device code only with -DRP_COOP (NOT the default build
+// of round 1: the protocol below is validated on the host, the device mapping has not run on a GPU yet), and into the host
+// counting build, where the "lanes" are a plain loop.
+#if defined(RP_COOP) || (defined(RP_COUNT) && !defined(__CUDA_ARCH__))
+#define RP_COOP_ON 1
+#define RP_COOPX(...) __VA_ARGS__
+#else
+#define RP_COOPX(...)
+#endif
+
 namespace poasta {
 namespace replay {
 
@@ -143,6 +153,17 @@ struct Result {
     uint32_t n_pairs;  // pairs are written BACKWARDS from out_r[cap-1]; the alignment is out_r[cap-n .. cap)
     int status;
     uint32_t num_queued, num_visited, num_pruned;
+};
+
+// One batch of the bucket-parallel evaluation: the top items of the stack being popped, one per lane, with the outcome of
+// the read-only half of their visit (the prune test) and what that outcome depended on. Shared memory on the device.
+constexpr uint32_t COOP_LANES = 32, COOP_EXITS = 4;
+struct CoopBatch {
+    uint32_t cmd;    // device: 0 idle, 1 evaluate, 2 worker finished (written by lane 0, read by the helper lanes)
+    uint32_t n, st, f;  // items in the batch; state type and priority of the stack they came from
+    uint32_t slot[COOP_LANES], node[COOP_LANES], off[COOP_LANES], score[COOP_LANES];
+    uint32_t pruned[COOP_LANES], n_exit[COOP_LANES];              // n_exit > COOP_EXITS: never reused
+    uint32_t exit[COOP_LANES][COOP_EXITS], epoch[COOP_LANES][COOP_EXITS];  // enclosing bubbles' exits and their epochs at evaluation
 };
 
 template <typename CellT> struct CellTraits;
@@ -284,49 +305,93 @@ struct Search {
     int err = RP_OK;
     // counting builds: how predictable is the next pop? (the item below the popped one / an item queued since / anything else)
     RP_STAT(uint32_t stat_below = 0; uint32_t stat_pushes_at_pop = 0; uint32_t stat_pushes = 0;)
-    // counting builds: MODEL of the bucket-parallel evaluation planned for the device. With spec_K > 0 the
-    // read-only half of a visit (stale test + prune test) is evaluated for the top spec_K items of the stack being popped as
-    // if by spec_K lanes at once; the sequential committer reuses a result only if no reached mark / reached score changed
-    // since (spec_epoch) and the items come off the stack in the predicted order. Checked against a fresh evaluation.
-    RP_STAT(struct Spec { uint32_t slot, node, off, st, score, n_exit, exit[4], epoch[4]; bool pruned; };
-            std::vector<uint32_t> spec_exit_epoch;  // per node: bumped when one of its reached marks / reached scores changes
-            Spec spec[64]; uint32_t spec_n = 0, spec_i = 0, spec_K = 0, spec_f = 0, spec_st = 0; const Spec *cur_spec = nullptr;
-            bool prune_pure(uint32_t score, uint32_t node, uint32_t off, uint32_t st) const {
-                const NodeA a = node_a(node);
-                const uint32_t nb = a.counts >> 16;
-                if (nb == 0) return false;
-                const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
-                return prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score) == 1;
-            }
-            void spec_on_pop(uint32_t slot, uint32_t st, uint32_t f) {
-                cur_spec = nullptr;
-                if (!spec_K) return;
-                if (spec_i < spec_n && spec[spec_i].slot == slot) {
-                    cur_spec = &spec[spec_i++];
-                    return;
-                }
-                // a pop from another stack (e.g. the Match state a popped gap state just closed into) leaves the batch alone:
-                // the committer handles that state on its own and comes back to the batch's stack afterwards
-                if (spec_i < spec_n && (f != spec_f || st != spec_st)) return;
-                if (spec_i < spec_n) RP_CNT(C_SPEC_ORDER_MISS);
-                spec_f = f, spec_st = st;
-                spec_n = spec_i = 0;
-                if (spec_exit_epoch.empty()) spec_exit_epoch.assign(g.V, 0);
-                for (uint32_t sl = slot;;) {  // "lanes" 0..K-1 take the items from the top of this stack downwards
-                    const Item it = s.items[sl];
-                    Spec sp{sl, it.node, it.offset, st, it.score, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, prune_pure(it.score, it.node, it.offset, st)};
-                    const NodeA a = node_a(it.node);
-                    const uint32_t nb = a.counts >> 16;
-                    sp.n_exit = nb;  // more than 4 enclosing bubbles: never reused
-                    for (uint32_t b = 0; b < nb && b < 4; ++b) sp.exit[b] = g.bub[a.bub_off + b].exit, sp.epoch[b] = spec_exit_epoch[sp.exit[b]];
-                    spec[spec_n++] = sp;
-                    if (spec_n >= spec_K || spec_n >= 64 || !it.next) break;
-                    sl = it.next - 1;
-                }
-                RP_CNT(C_SPEC_BATCH);
-                rp_counters[C_SPEC_ITEMS] += spec_n;
-                cur_spec = &spec[spec_i++];
-            })
+    // ---- bucket-parallel evaluation -------------------------------------------------------------------
+    // The prune test of the top coop_K items of the stack being popped is evaluated by coop_K lanes at once (device: the
+    // helper lanes of the warp; host: a loop); lane 0, which alone changes state, commits the items in the reference's
+    // order and reuses a result only if (a) the item comes off the stack in the predicted order - pops from other stacks
+    // in between leave the batch alone - and (b) none of its bubbles' exits had a reached mark or a reached score changed
+    // since (exit_epoch). tests/test_replay_core_host.py checks every reused result against a fresh evaluation.
+    RP_COOPX(CoopBatch *coop = nullptr;      // nullptr: disabled
+             uint32_t *exit_epoch = nullptr; // per node, zeroed per alignment
+             uint32_t coop_K = 0, coop_i = 0;
+             int cur_spec = -1;)             // batch index of the item just popped, -1 = evaluate normally
+#if defined(RP_COOP_ON)
+    RP_HD bool prune_pure(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) const {
+        const uint32_t nb = a.counts >> 16;
+        if (nb == 0) return false;
+        const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
+        return prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score) == 1;
+    }
+    // what lane l does in the parallel phase: read-only on the alignment's state, writes only its own batch entries
+    RP_HD void coop_eval_lane(uint32_t l) const {
+        CoopBatch &b = *coop;
+        if (l >= b.n) return;
+        const Item it = s.items[b.slot[l]];
+        const NodeA a = node_a(it.node);
+        const uint32_t nb = a.counts >> 16;
+        b.node[l] = it.node, b.off[l] = it.offset, b.score[l] = it.score;
+        b.n_exit[l] = nb;
+        for (uint32_t k = 0; k < nb && k < COOP_EXITS; ++k) {
+            const uint32_t x = g.bub[a.bub_off + k].exit;
+            b.exit[l][k] = x, b.epoch[l][k] = exit_epoch[x];
+        }
+        b.pruned[l] = prune_pure(it.score, it.node, a, it.offset, b.st) ? 1u : 0u;
+    }
+    RP_HD void coop_phase() {
+#if defined(__CUDA_ARCH__)
+        *(volatile uint32_t *)&coop->cmd = 1;
+        __syncwarp();  // releases the helper lanes (replay_kernel.cuh), which see the batch written above
+        coop_eval_lane(0);
+        __syncwarp();  // their results are visible from here on
+#else
+        for (uint32_t l = 0; l < coop->n; ++l) coop_eval_lane(l);
+#endif
+    }
+    RP_HD void coop_on_pop(uint32_t slot, uint32_t st, uint32_t f) {
+        cur_spec = -1;
+        if (!coop || !coop_K) return;
+        CoopBatch &b = *coop;
+        if (coop_i < b.n && b.slot[coop_i] == slot) {
+            cur_spec = (int)coop_i++;
+            return;
+        }
+        // a pop from another stack (e.g. the Match state a popped gap state just closed into) leaves the batch alone:
+        // lane 0 handles that state on its own and comes back to the batch's stack afterwards
+        if (coop_i < b.n && (f != b.f || st != b.st)) return;
+        if (coop_i < b.n) RP_CNT(C_SPEC_ORDER_MISS);
+        b.f = f, b.st = st;
+        uint32_t n = 0;
+        for (uint32_t sl = slot;;) {  // lanes 0..K-1 take the items from the top of this stack downwards
+            b.slot[n++] = sl;
+            const uint32_t next = s.items[sl].next;
+            if (n >= coop_K || n >= COOP_LANES || !next) break;
+            sl = next - 1;
+        }
+        b.n = n;
+        coop_i = 0;
+        coop_phase();
+        RP_CNT(C_SPEC_BATCH);
+        RP_STAT(rp_counters[C_SPEC_ITEMS] += n;)
+        cur_spec = (int)coop_i++;
+    }
+    // result of the batch entry of the state just popped if it is still valid, else -1
+    RP_HD int coop_lookup(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {
+        if (cur_spec < 0) return -1;
+        const CoopBatch &b = *coop;
+        const uint32_t l = (uint32_t)cur_spec;
+        cur_spec = -1;
+        if (b.node[l] != node || b.off[l] != off || b.st != st || b.score[l] != score) return -1;
+        bool fresh = b.n_exit[l] <= COOP_EXITS;
+        for (uint32_t k = 0; k < b.n_exit[l] && k < COOP_EXITS; ++k) fresh = fresh && exit_epoch[b.exit[l][k]] == b.epoch[l][k];
+        if (!fresh) {
+            RP_CNT(C_SPEC_EPOCH_MISS);
+            return -1;
+        }
+        RP_CNT(C_SPEC_REUSED);
+        if (b.pruned[l]) RP_CNT(C_SPEC_REUSED_PRUNED);
+        return (int)b.pruned[l];
+    }
+#endif
 #if defined(RP_PROFILE)
     long long prof_prune = 0, prof_push = 0, prof_pop = 0;
     uint32_t prof_n_prune = 0;
@@ -362,8 +427,7 @@ struct Search {
         RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
             RP_CNT(C_RELAX_OK);
-            RP_STAT(if ((cur & FLAG) && !spec_exit_epoch.empty())
-                        ++spec_exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
+            RP_COOPX(if ((cur & FLAG) && exit_epoch) ++exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
             *c = (CellT)((CellT)v | (CellT)(cur & FLAG));  // a reached offset stays reached when its score improves
             return true;
         }
@@ -380,8 +444,7 @@ struct Search {
         RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
             RP_CNT(C_RELAX_OK);
-            RP_STAT(if ((cur & FLAG) && !spec_exit_epoch.empty())
-                        ++spec_exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
+            RP_COOPX(if ((cur & FLAG) && exit_epoch) ++exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
             *c = (CellT)((CellT)v | (CellT)(cur & FLAG));
             return true;
         }
@@ -486,7 +549,7 @@ struct Search {
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
-                    RP_STAT(spec_on_pop(slot, k, f_cur);)
+                    RP_COOPX(coop_on_pop(slot, k, f_cur);)
                     RP_STAT(if (slot + 1 == stat_below) RP_CNT(C_NEXT_SAME_STACK);
                             else if (stat_pushes != stat_pushes_at_pop) RP_CNT(C_NEXT_JUST_PUSHED);  // approximation: something was queued since
                             else RP_CNT(C_NEXT_OTHER);
@@ -508,7 +571,7 @@ struct Search {
     // ---- reached marks (BTreeSet<offset> per exit; gap_affine.rs:767-773) -------------------------------
     RP_HD void mark_reached(uint32_t node, bool is_exit, uint32_t off, uint32_t st) {
         if (st == ST_M && is_exit) {
-            RP_STAT(if (!spec_exit_epoch.empty()) ++spec_exit_epoch[node];)
+            RP_COOPX(if (exit_epoch) ++exit_epoch[node];)
             *cell(node, off, ST_M) |= FLAG;
             uint32_t *b = s.rb + 2 * (size_t)node;
             if (b[1] == 0) {
@@ -521,19 +584,13 @@ struct Search {
     }
 
     RP_HD bool prune(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
-        RP_STAT(if (cur_spec && cur_spec->node == node && cur_spec->off == off && cur_spec->st == st && cur_spec->score == score) {
-                    const Spec *sp = cur_spec;
-                    cur_spec = nullptr;
-                    bool fresh = sp->n_exit <= 4;
-                    for (uint32_t b = 0; b < sp->n_exit && b < 4; ++b) fresh = fresh && spec_exit_epoch[sp->exit[b]] == sp->epoch[b];
-                    if (fresh) {
-                        RP_CNT(C_SPEC_REUSED);
-                        if (sp->pruned) RP_CNT(C_SPEC_REUSED_PRUNED);
-                        if (prune_pure(score, node, off, st) != sp->pruned) RP_CNT(C_SPEC_WRONG);
-                        return sp->pruned;
-                    }
-                    RP_CNT(C_SPEC_EPOCH_MISS);
-                })
+        RP_COOPX({
+            const int hit = coop_lookup(score, node, off, st);
+            if (hit >= 0) {
+                RP_STAT(if (prune_pure(score, node, a, off, st) != (hit == 1)) RP_CNT(C_SPEC_WRONG);)
+                return hit == 1;
+            }
+        })
         const uint32_t nb = a.counts >> 16;
         if (nb == 0) return false;
         RP_T0;

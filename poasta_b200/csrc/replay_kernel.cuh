@@ -27,6 +27,9 @@ struct ReplayDev {
     replay::Params prm;
     uint8_t *slabs;
     uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_dfa;  // byte offsets inside a slab (score planes at 0)
+#if defined(RP_COOP)
+    uint64_t off_epoch;  // per-node epochs of the bucket-parallel evaluation (replay_core.hpp)
+#endif
     uint32_t max_items;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
@@ -40,6 +43,9 @@ constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few worke
 template <typename CellT, int MINB, int HEUR>
 __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
     __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];  // queue-head window of each worker
+#if defined(RP_COOP)
+    __shared__ replay::CoopBatch s_coop[REPLAY_MAX_WARPS_PER_CTA];  // batch of the bucket-parallel evaluation of each worker
+#endif
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
@@ -65,9 +71,21 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             const uint32_t n2 = ((uint64_t)gd.V * 2 + 3) / 4;
             for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
             for (uint32_t i = lane; i < replay::QWIN * 3; i += 32) s_qwin[wib][i] = 0;
+#if defined(RP_COOP)
+            uint4 *p3 = reinterpret_cast<uint4 *>(slab + B.off_epoch);
+            const uint32_t n3 = ((uint64_t)gd.V + 3) / 4;
+            for (uint32_t i = lane; i < n3; i += 32) p3[i] = z;
+            if (lane == 0) s_coop[wib].cmd = 0, s_coop[wib].n = 0;
+#endif
         }
         __syncwarp();
-        if (lane == 0) {
+#if defined(RP_COOP)
+        // every lane holds the (read-only) view of the alignment; lane 0 runs the state machine, lanes 1..31 wait for batches
+        constexpr bool all_lanes = true;
+#else
+        constexpr bool all_lanes = false;
+#endif
+        if (lane == 0 || all_lanes) {
             replay::Graph g;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
             g.nodes = B.nodes + gd.node_base;
@@ -91,6 +109,21 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             const long long t_begin = clock64();
 #endif
             replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
+#if defined(RP_COOP)
+            search.coop = &s_coop[wib];
+            search.exit_epoch = reinterpret_cast<uint32_t *>(slab + B.off_epoch);
+            search.coop_K = replay::COOP_LANES;
+            if (lane != 0) {
+                // helper lane: one evaluation per batch lane 0 announces (two __syncwarp per batch on both sides,
+                // replay_core.hpp coop_phase), until lane 0 reports the end of the alignment
+                for (;;) {
+                    __syncwarp();
+                    if (*(volatile uint32_t *)&s_coop[wib].cmd == 2) break;
+                    search.coop_eval_lane(lane);
+                    __syncwarp();
+                }
+            } else {
+#endif
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;
@@ -105,6 +138,11 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
                            a, total, search.prof_prune, 100.0 * search.prof_prune / total, search.prof_n_prune,
                            search.prof_prune / (search.prof_n_prune ? search.prof_n_prune : 1), search.prof_push,
                            100.0 * search.prof_push / total, r.num_visited, r.num_queued, r.num_pruned, total / (r.num_visited ? r.num_visited : 1));
+            }
+#endif
+#if defined(RP_COOP)
+            *(volatile uint32_t *)&s_coop[wib].cmd = 2;
+            __syncwarp();  // releases the helper lanes for the last time
             }
 #endif
         }
