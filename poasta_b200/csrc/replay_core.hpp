@@ -15,24 +15,23 @@
 //   backtrace              /root/reference/src/aligner/scoring/gap_affine.rs:550-657, 804-915
 //
 // Device mapping: the state machine is sequential per alignment, so one warp owns one alignment and
-// lane 0 drives it (10^4 families in flight = 10^4 warps). A worker is bound by dependent DRAM misses
-// (measured: ~24k cycles per visited state with one array per attribute), so the layout is built to
-// need few of them:
+// lane 0 drives it (10^4 families in flight = 10^4 warps). A worker is ONE thread walking a chain of
+// ~260 dependent instructions and a handful of dependent loads per popped state (profiles/README.md:
+// ~9 cycles per issued instruction, a third of it memory), so both the code and the layout are kept short:
 //   node record    32 B per node: successor / bubble list ranges, symbol, is-exit, distances to `end`,
 //                  predecessor range - one sector instead of seven arrays
-//   visited table  three dense planes (M, D, I) of V x W scores, u16 when every reachable score fits;
-//                  the top bit of a Match cell is the "reached" mark of the prune test (the reference's
-//                  BTreeSet<offset> per bubble exit), so marking costs no extra access and a prune
-//                  query reads flags and scores from the same cache lines; [lo, hi] bounds per node
-//                  keep the scans inside the occupied band
+//   visited table  dense V x W records {M, D, I, pad} (u16 cells when every reachable score fits): a popped
+//                  state and the states it relaxes share a sector; the top bit of a Match cell is the
+//                  "reached" mark of the prune test (the reference's BTreeSet<offset> per bubble exit), so
+//                  marking costs no extra access and a prune query reads flags and scores from the same
+//                  cache lines; [lo, hi] bounds per node keep the scans inside the occupied band
 //   bucket queue   three LIFO stacks per priority threaded through a 16-byte item array with a free
 //                  list; the heads of the 64 priorities around the current one live in shared memory
+//   code           the heuristic is a template parameter and every "relax, queue if improved" step goes
+//                  through one site, which halved the kernel (instruction fetch was 20-30 % of its stalls)
 // The same source compiles for the host (tests only) so the logic can be checked without a GPU.
 #pragma once
 #include <cstdint>
-#if defined(RP_COUNT) && !defined(__CUDA_ARCH__)
-#include <vector>
-#endif
 
 #if defined(__CUDACC__)
 #define RP_HD __host__ __device__ __forceinline__
