@@ -213,3 +213,13 @@ def test_int_peak_probe_and_device_time():
     crit = aligner.last_batch_device_ms()
     kms, launches, cells = aligner.last_batch_stats()
     assert 0.0 < crit <= kms + aligner.last_batch_search_ms() + 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_test", "test_from_abpoa", "test2_from_abpoa"])
+def test_msa_reproduces_committed_golden_outputs(name):
+    """The reference's own test inputs through the CUDA path against the committed golden bytes (tools/make_golden.py)."""
+    fasta = open(f"tests/golden/{name}.fa", "rb").read()
+    graphs, scores, cells = msa_batch([fasta])
+    assert graphs[0].to_fasta() == open(f"tests/golden/{name}.expected.fa", "rb").read()
+    assert graphs[0].to_gfa() == open(f"tests/golden/{name}.expected.gfa", "rb").read()
+    assert [int(s) for s in scores[0]] == [int(x) for x in open(f"tests/golden/{name}.expected.scores").read().split()]
