@@ -72,6 +72,8 @@ struct PackedGraph {
         rank_scratch.resize(V);
         for (uint32_t r = 0; r < V; ++r) rank_scratch[g.topo_order[r]] = r;
         node_sym.clear(), node_info.clear(), node_id.clear(), ord_slot.clear(), pred_off.clear(), pred_rank.clear(), pred_slot.clear();
+        node_sym.reserve(V), node_info.reserve(V), node_id.reserve(V), ord_slot.reserve(V), pred_off.reserve(V + 1);
+        pred_rank.reserve(g.pred_off[V]);
         max_in_degree = n_stored = n_ord_rows = 0;
         for (uint32_t r = 0; r < V; ++r) {
             const uint32_t v = g.topo_order[r];
