@@ -520,6 +520,7 @@ struct AstarData {
     const BubbleIndex &bubbles;
     VisitedStore visited;
     std::vector<std::set<uint32_t>> reached_m;
+    std::vector<uint32_t> *pruned_log = nullptr;  // diagnostics (tools/tie_study.cpp): (node, offset, state) of every pruned state
 
     AstarData(const Graph &graph, Costs c, size_t qlen, const BubbleIndex &b)
         : g(graph), costs(c), seq_len(qlen), bubbles(b), visited(graph), reached_m(graph.n()) {}
@@ -620,7 +621,10 @@ struct AstarData {
         const auto &bs = bubbles.node_bubble_map[node];
         if (bs.empty()) return false;
         for (const auto &b : bs)
-            if (!can_improve_bubble(b, node, offset, st, score)) return true;  // !all(...)
+            if (!can_improve_bubble(b, node, offset, st, score)) {  // !all(...)
+                if (pruned_log) pruned_log->insert(pruned_log->end(), {node, offset, (uint32_t)st});
+                return true;
+            }
         return false;
     }
 
@@ -843,6 +847,8 @@ struct AlignOptions {
     bool mock = false;
     // optional: dump of the visited table for diagnostics (tests only)
     std::vector<uint32_t> *dump = nullptr;  // (node, offset, state, score)*
+    std::vector<uint32_t> *pruned_log = nullptr;  // (node, offset, state)* of pruned states
+    std::vector<uint32_t> *pop_log = nullptr;     // (node, offset, state, score)* of expanded (popped, not stale, not pruned) states
 };
 
 // gap_affine.rs:185-248 with the four bounds Unbounded (what the CLI passes)
@@ -872,6 +878,7 @@ inline AstarResult astar_align(const poasta_graph_view &view, const uint8_t *seq
             heur.paths = pidx.get();
         }
         AstarData vis(g, opt.costs, qlen, bubbles);
+        vis.pruned_log = opt.pruned_log;
         AffineQueue queue;
         const Costs &c = opt.costs;
 
@@ -914,6 +921,7 @@ inline AstarResult astar_align(const poasta_graph_view &view, const uint8_t *seq
             vis.mark_reached(it.node, it.offset, it.state);
             ++res.num_visited;
             const uint32_t score = it.score;
+            if (opt.pop_log) opt.pop_log->insert(opt.pop_log->end(), {it.node, it.offset, (uint32_t)it.state, score});
             if (it.state == MATCH) {
                 DepthFirstGreedyAlignment<AstarData> dfa(g, seq, qlen, score, it.node, it.offset);
                 for (;;) {
