@@ -69,18 +69,24 @@ typedef struct poasta_result {
     uint32_t *qpos;
     uint32_t capacity;
     int32_t status;     /* poasta_status of this alignment                                */
-    uint64_t num_cells; /* reported in place of num_visited: DP cells filled              */
+    uint64_t num_cells; /* (real nodes) x (query length): the cell count GCUPS is quoted on */
+    /* AstarResult.num_queued / num_visited / num_pruned (aligner/astar.rs:81-90) as the order-exact search counted
+     * them (tiebreak = 0; tests/test_heuristics.rs:53-56,142 read them). 0 with tiebreak = 1: the DP fill has no queue. */
+    uint64_t num_queued, num_visited, num_pruned;
 } poasta_result;
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 
 /* Replaces PoastaAligner::align::<u32,_>(&graph, seq) (aligner/mod.rs:114-145) for a batch of
  * independent (graph, query) problems on one device: alignment i aligns queries[i] against
- * graphs[graph_of_query[i]]. Blocking; thread-safe per device. */
+ * graphs[graph_of_query[i]]. Blocking. */
 int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_graphs,
                        const uint8_t *const *queries, const uint32_t *qlens,
                        const uint32_t *graph_of_query, uint32_t n_queries,
                        const poasta_params *params, poasta_result *results);
+/* Threading: any host thread may call; calls that name the same `device` are serialised inside the library for their
+ * whole duration (they share that device's streams and buffers), calls on different devices run concurrently.
+ * 0 <= device < 16. */
 
 /* Timing of the device work of the last poasta_align_batch on this thread (CUDA events on the
  * launching stream): milliseconds of the fill+traceback kernels, number of launches, cells. */
@@ -91,6 +97,9 @@ int poasta_last_batch_search_ms(double *search_ms);
  * the pipeline lanes run their kernels concurrently, so this is the LARGEST per-lane sum (the device-side critical path
  * of the call), whereas poasta_last_batch_stats / _search_ms report the sums over all lanes. */
 int poasta_last_batch_device_ms(double *device_ms);
+/* num_queued / num_visited / num_pruned summed over every alignment of the last poasta_msa_batch* on this thread
+ * (reference-exact mode). */
+int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited, uint64_t *num_pruned);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Measured integer issue peaks of `device` in 10^12 lane-operations per second: 32-bit add, xor+min pairs (2 operations),

@@ -357,13 +357,24 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     // generous arena for the host build: every state can be queued once per successful relaxation
     const uint32_t max_items = 3 * view->n_nodes * (qlen + 2) + 65536;
     const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
-    std::vector<uint8_t> planes((size_t)rp::CELL_SLOTS * plane_elems * (cell16 ? 2 : 4));
-    if (cell16) std::fill((uint16_t *)planes.data(), (uint16_t *)planes.data() + rp::CELL_SLOTS * plane_elems, (uint16_t)0x7FFF);
-    else std::fill((uint32_t *)planes.data(), (uint32_t *)planes.data() + rp::CELL_SLOTS * plane_elems, 0x7FFFFFFFu);
+    // records {M, D, I, epoch}: zero-filled = "written by no alignment"; this alignment runs as epoch 1 (RP_HOST_EPOCH overrides
+    // it and pre-fills the table with records of OTHER epochs, to check that stale records read as unvisited)
+    std::vector<uint8_t> planes((size_t)4 * plane_elems * (cell16 ? 2 : 4), 0);
+    uint32_t epoch = 1;
+    if (const char *ep = getenv("RP_HOST_EPOCH")) {
+        epoch = (uint32_t)atoi(ep);
+        uint32_t x = 12345;
+        for (size_t i = 0; i < planes.size(); i += (cell16 ? 8 : 16)) {  // garbage scores stamped with epochs != epoch
+            for (int k = 0; k < (cell16 ? 8 : 16); ++k) planes[i + k] = (uint8_t)((x = x * 1664525u + 1013904223u) >> 24);
+            uint32_t other = (x >> 8) % 0xFFFEu + 1;
+            if (other == epoch) other = epoch == 1 ? 2 : epoch - 1;
+            if (cell16) ((uint16_t *)(planes.data() + i))[3] = (uint16_t)other;
+            else ((uint32_t *)(planes.data() + i))[3] = other;
+        }
+    }
     std::vector<Item> items(max_items);
     std::vector<uint32_t> free_slots(max_items);
-    Scratch s{planes.data(), qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), plane_elems, d.W,
-              max_items, d.f_max};
+    Scratch s{planes.data(), epoch, qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), d.W, max_items, d.f_max};
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
@@ -371,11 +382,6 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     uint32_t used_blocks = 0, used_items = 0;
     auto go = [&](auto cell, auto heur) {
         rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
-        rp::CoopBatch batch{};
-        std::vector<uint32_t> epochs(view->n_nodes, 0);
-        if (const char *k = getenv("RP_SPEC_K")) {  // bucket-parallel evaluation with K lanes (the host runs them as a loop)
-            search.coop = &batch, search.exit_epoch = epochs.data(), search.coop_K = (uint32_t)atoi(k);
-        }
         r = search.run(out_r.data(), out_q.data(), ocap);
         used_items = search.n_items;
     };

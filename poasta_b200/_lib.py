@@ -32,12 +32,13 @@ class Result(C.Structure):
     """``poasta_result``: AstarResult (aligner/astar.rs:81-90)."""
     _fields_ = [("score", C.c_uint32), ("n_pairs", C.c_uint32),
                 ("rpos", C.POINTER(C.c_uint32)), ("qpos", C.POINTER(C.c_uint32)),
-                ("capacity", C.c_uint32), ("status", C.c_int32), ("num_cells", C.c_uint64)]
+                ("capacity", C.c_uint32), ("status", C.c_int32), ("num_cells", C.c_uint64),
+                ("num_queued", C.c_uint64), ("num_visited", C.c_uint64), ("num_pruned", C.c_uint64)]
 
 
 # every symbol include/poasta_b200.h declares
 EXPORTS = [
-    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_batch_io", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
+    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_batch_io", "poasta_last_batch_search_counts", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
     "poasta_graph_new", "poasta_graph_free", "poasta_graph_node_count",
     "poasta_graph_node_count_with_start_and_end", "poasta_graph_edge_count",
     "poasta_graph_num_sequences", "poasta_graph_add_alignment", "poasta_graph_get_view",
@@ -84,6 +85,7 @@ def load():
     lib.poasta_last_batch_search_ms.argtypes = [C.POINTER(C.c_double)]
     lib.poasta_last_batch_io.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.poasta_last_batch_device_ms.argtypes = [C.POINTER(C.c_double)]
+    lib.poasta_last_batch_search_counts.argtypes = [C.POINTER(C.c_uint64)] * 3
     lib.poasta_measure_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.poasta_msa_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32,
                                      C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(C.c_uint64)]

@@ -51,12 +51,14 @@ class AffinePathAware:
 
 @dataclass
 class AstarResult:
-    """aligner/astar.rs:81-90. num_queued/num_pruned are A*-specific and reported as 0; num_visited = DP cells."""
+    """aligner/astar.rs:81-90. The three counters are the order-exact search's (0 in DP-only mode); num_cells = real nodes x query
+    length, the unit GCUPS is quoted on."""
     score: int
     alignment: list
     num_queued: int = 0
     num_visited: int = 0
     num_pruned: int = 0
+    num_cells: int = 0
     rpos: np.ndarray = field(default=None, repr=False)
     qpos: np.ndarray = field(default=None, repr=False)
 
@@ -102,7 +104,8 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
         k = results[i].n_pairs
         r, q = bufs[i][0][:k].copy(), bufs[i][1][:k].copy()
         aln = [AlignedPair(None if a == NONE else int(a), None if b == NONE else int(b)) for a, b in zip(r, q)]
-        out.append(AstarResult(int(results[i].score), aln, 0, int(results[i].num_cells), 0, r, q))
+        out.append(AstarResult(int(results[i].score), aln, int(results[i].num_queued), int(results[i].num_visited),
+                               int(results[i].num_pruned), int(results[i].num_cells), r, q))
     return out
 
 
@@ -126,6 +129,14 @@ def last_batch_device_ms():
     ms = C.c_double()
     lib.poasta_last_batch_device_ms(C.byref(ms))
     return ms.value
+
+
+def last_batch_search_counts():
+    """(num_queued, num_visited, num_pruned) summed over the last msa_batch in reference-exact mode."""
+    lib = _lib.load()
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.poasta_last_batch_search_counts(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
 
 
 def last_batch_io():
@@ -159,7 +170,7 @@ def msa_batch(fastas, config=AffineMinGapCost(), aln_type=AlignmentType.Global, 
     fa = [f if isinstance(f, bytes) else f.encode() for f in fastas]
     ptr = (C.c_char_p * n)(*fa)
     lens = (C.c_size_t * n)(*[len(f) for f in fa])
-    nseq = [f.count(b">") for f in fa]
+    nseq = [int(f.startswith(b">")) + f.count(b"\n>") for f in fa]  # '>' at line starts only, like the C side
     scores = np.zeros(max(1, sum(nseq)), np.uint32)
     cells = C.c_uint64()
     prm = _params(config, aln_type, tiebreak)

@@ -24,6 +24,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -32,6 +34,7 @@
 #include "device_batch.hpp"
 #include "graph_handle.hpp"
 #include "replay_kernel.cuh"
+#include "msa_engine.cuh"
 
 namespace poasta {
 
@@ -423,6 +426,10 @@ struct DeviceContext {
         n_pairs, status, offsets, dense_r, dense_q;
     PinBuf h_scores, h_npairs, h_status, h_offsets, h_dense_r, h_dense_q, h_in;
     Buf r_graphs, r_nodes, r_succ, r_pred, r_bub, r_path_off, r_path_rem, r_slabs, r_stats;
+    // what the search slabs were last laid out for: worker slabs keep their epoch-stamped tables across launches and are
+    // zeroed only when the buffer moves or the layout / cell width changes (replay_kernel.cuh SlabHeader)
+    void *slab_ptr = nullptr;
+    uint64_t slab_sig = 0, slab_zeroed_bytes = 0;
     PinBuf h_stats;
     double last_kernel_ms = 0;
     uint32_t last_launches = 0;
@@ -454,11 +461,19 @@ struct DeviceContext {
 constexpr int MAX_LANES = 32;
 static thread_local int tl_lane = 0;        // pipeline lane of the calling thread
 static thread_local int tl_lane_count = 1;  // lanes sharing the device right now (memory budgets are divided by it)
-static DeviceContext &ctx_for(int device) {
+constexpr int MAX_DEVICES = 16;
+static DeviceContext &ctx_for(int device) {  // callers have checked 0 <= device < MAX_DEVICES
     static std::mutex mu;
-    static DeviceContext ctxs[16][MAX_LANES];
+    static DeviceContext ctxs[MAX_DEVICES][MAX_LANES];
     std::lock_guard<std::mutex> lk(mu);
-    return ctxs[device & 15][tl_lane % MAX_LANES];
+    return ctxs[device][tl_lane % MAX_LANES];
+}
+// One public call at a time per device: the contexts (streams, grow-only device buffers, pinned staging) of a device are
+// shared by every host thread that names it, so concurrent callers are serialised here for the WHOLE call. Different
+// devices run concurrently. (Pipeline lanes inside one call use separate contexts.)
+static std::mutex &device_call_mutex(int device) {
+    static std::mutex mus[MAX_DEVICES];
+    return mus[device];
 }
 
 static thread_local double tl_kernel_ms = 0, tl_search_ms = 0;
@@ -466,6 +481,8 @@ static thread_local double tl_lane_max_ms = -1;  // msa batches: the largest per
 static thread_local uint32_t tl_launches = 0;
 static thread_local uint64_t tl_cells = 0;
 static thread_local uint64_t tl_h2d = 0, tl_d2h = 0;
+static thread_local uint64_t tl_engine_counts[3] = {0, 0, 0};  // queued, visited, pruned summed over the last msa batch (reference-exact mode)
+static thread_local std::vector<uint32_t> tl_search_stats;  // per problem of the last align batch: queued, visited, pruned (search path only)
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -489,6 +506,10 @@ static cudaError_t wait_stream(DeviceContext &c) {
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(c.ev_done);
 }
+
+}  // namespace poasta
+#include "msa_engine_host.cuh"
+namespace poasta {
 
 // Runs one packed batch (must fit the memory budget) and leaves results in pinned host memory.
 static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_params &prm, ChunkResult &res, bool scores_only) {
@@ -738,7 +759,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
     const bool cell16 = worst < 0x7F00u;  // the top bit of a cell is the reached mark
-    const uint64_t plane_bytes = up(replay::CELL_SLOTS * cells_per_aln * (cell16 ? 2 : 4));
+    const uint64_t plane_bytes = up(4 * cells_per_aln * (cell16 ? 2 : 4));  // records {M, D, I, epoch}
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
     // (the inadmissible path heuristic on divergent input re-queues states: high-water 0.99 x cells seen in tools/fuzz_core_vs_oracle.py)
@@ -749,16 +770,12 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     static const double slab_fraction = getenv("POASTA_SLAB_FRACTION") ? atof(getenv("POASTA_SLAB_FRACTION")) : 0.6;
     const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(slab_fraction * (double)total_b)) / tl_lane_count;
     uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_dfa = 0;
-    off_qhead = plane_bytes;
+    off_qhead = SLAB_CELLS + plane_bytes;
     off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
     off_free = off_items + up(max_items * 16);
     off_reached = off_free + up(max_items * 4);                   // reached bounds: 2 words per node
     off_dfa = off_reached + up((uint64_t)pr.max_V * 8);
     slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);           // DFA frames: 6 words
-#if defined(RP_COOP)
-    const uint64_t off_epoch = slab;                               // per-node epochs of the bucket-parallel evaluation
-    slab += up((uint64_t)pr.max_V * 4);
-#endif
     const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
     const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
@@ -766,6 +783,14 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     if (!c.r_slabs.reserve(workers * slab)) {
         workers = warps_per_cta;
         if (!c.r_slabs.reserve(workers * slab)) return POASTA_ERR_CUDA;
+    }
+    {
+        const uint64_t sig = slab * 1000003ull + off_qhead * 10007ull + off_items * 101ull + off_dfa + (cell16 ? 1ull << 62 : 0);
+        if (c.slab_ptr != c.r_slabs.d || c.slab_sig != sig) c.slab_ptr = c.r_slabs.d, c.slab_sig = sig, c.slab_zeroed_bytes = 0;
+        if (workers * slab > c.slab_zeroed_bytes) {
+            CK(cudaMemsetAsync((uint8_t *)c.r_slabs.d + c.slab_zeroed_bytes, 0, workers * slab - c.slab_zeroed_bytes, c.stream));
+            c.slab_zeroed_bytes = workers * slab;
+        }
     }
     bool ok = c.r_graphs.reserve(pr.graphs.size() * sizeof(RGraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.r_nodes.reserve(pr.nodes.size() * sizeof(replay::NodeRec) + 32) && c.queries.reserve(pr.queries.size() + 4) &&
@@ -806,9 +831,6 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.slabs = (uint8_t *)c.r_slabs.d;
     B.slab_bytes = slab;
     B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_dfa = off_dfa;
-#if defined(RP_COOP)
-    B.off_epoch = off_epoch;
-#endif
     B.max_items = (uint32_t)max_items;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;
@@ -909,6 +931,8 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
         int32_t status = 0;
         std::vector<uint32_t> r, q;
     };
+    tl_search_stats.assign(probs.size() * 3, 0);
+    std::vector<uint32_t> launch_stats;
     std::vector<Out> outs(probs.size());
     std::vector<size_t> todo;
     for (size_t i = 0; i < probs.size(); ++i) {
@@ -934,7 +958,7 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
             }
             pr.add_alignment(last_gid, p.query, p.qlen);
         }
-        rc = run_replay(c, pr, prm, res, nullptr, attempt == 1);
+        rc = run_replay(c, pr, prm, res, &launch_stats, attempt == 1);
         if (rc) return rc;
         std::vector<size_t> again;
         for (size_t k = 0; k < todo.size(); ++k) {
@@ -944,6 +968,7 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
                 continue;
             }
             Out &o = outs[todo[k]];
+            for (int t = 0; t < 3; ++t) tl_search_stats[todo[k] * 3 + t] = launch_stats[4 * k + t];
             o.score = res.scores[k];
             o.status = map_replay_status(st);
             o.r.assign(res.dense_r + res.offsets[k], res.dense_r + res.offsets[k] + res.n_pairs[k]);
@@ -1026,14 +1051,76 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int *out, int iters, int 
     if (r == 0x7FFFFFFF) out[blockIdx.x * blockDim.x + threadIdx.x] = r;  // practically never: keeps the work live
 }
 
+// Worker threads that live as long as the object; run(n, fn) hands out index blocks of 16 and returns when all are done.
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(size_t)> fn;
+    std::atomic<size_t> next{0};
+    size_t n = 0, generation = 0, busy = 0;
+    bool stop = false;
+    explicit HostPool(unsigned n_threads) {
+        for (unsigned t = 1; t < n_threads; ++t) threads.emplace_back([this]() { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    void drain() {
+        for (;;) {
+            const size_t i0 = next.fetch_add(16);
+            if (i0 >= n) break;
+            for (size_t i = i0; i < std::min(n, i0 + 16); ++i) fn(i);
+        }
+    }
+    void loop() {
+        size_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&]() { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            drain();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--busy == 0) cv_done.notify_all();
+            }
+        }
+    }
+    template <class F> void run(size_t count, F &&f) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = std::ref(f);
+            n = count;
+            next = 0;
+            busy = threads.size();
+            ++generation;
+        }
+        cv_work.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&]() { return busy == 0; });
+    }
+};
+
 extern "C" {
 
 int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_graphs, const uint8_t *const *queries,
                        const uint32_t *qlens, const uint32_t *graph_of_query, uint32_t n_queries, const poasta_params *params,
                        poasta_result *results) {
     if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
+    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
     tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
     tl_lane_max_ms = -1;
+    tl_search_stats.clear();
     std::vector<Problem> probs(n_queries);
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
@@ -1046,6 +1133,10 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
                               out.score = score;
                               out.status = status;
                               out.num_cells = (uint64_t)(probs[i].graph->n_nodes - 2) * probs[i].qlen;
+                              const bool have = tl_search_stats.size() == probs.size() * 3;  // empty with tiebreak = 1 (no search ran)
+                              out.num_queued = have ? tl_search_stats[3 * i] : 0;
+                              out.num_visited = have ? tl_search_stats[3 * i + 1] : 0;
+                              out.num_pruned = have ? tl_search_stats[3 * i + 2] : 0;
                               out.n_pairs = np;
                               if (np > out.capacity) {
                                   out.status = POASTA_ERR_INVALID_ARG;
@@ -1075,6 +1166,13 @@ int poasta_last_batch_device_ms(double *device_ms) {
     return 0;
 }
 
+int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited, uint64_t *num_pruned) {
+    if (num_queued) *num_queued = tl_engine_counts[0];
+    if (num_visited) *num_visited = tl_engine_counts[1];
+    if (num_pruned) *num_pruned = tl_engine_counts[2];
+    return 0;
+}
+
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = tl_h2d;
     if (d2h_bytes) *d2h_bytes = tl_d2h;
@@ -1082,6 +1180,8 @@ int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
 }
 
 int poasta_measure_int_peak(int device, double *add_tops, double *min_tops, double *addmin_tops) {
+    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
     DeviceContext &c = ctx_for(device);
     int rc = c.init(device);
     if (rc) return rc;
@@ -1131,22 +1231,13 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
         max_round = std::max(max_round, recs[f].size());
     }
     std::atomic<int> err{0};
+    HostPool pool(n_threads);  // one set of worker threads for the whole group (round 1 spawned and joined threads 38 times per step and lane)
     auto parallel_for = [&](size_t n, auto &&fn) {
         if (n < 64 || n_threads <= 1) {
             for (size_t i = 0; i < n; ++i) fn(i);
             return;
         }
-        std::atomic<size_t> next{0};
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < n_threads; ++t)
-            pool.emplace_back([&]() {
-                for (;;) {
-                    size_t i0 = next.fetch_add(16);
-                    if (i0 >= n) break;
-                    for (size_t i = i0; i < std::min(n, i0 + 16); ++i) fn(i);
-                }
-            });
-        for (auto &t : pool) t.join();
+        pool.run(n, fn);
     };
     uint64_t cells = 0;
     std::vector<Problem> probs;
@@ -1239,7 +1330,49 @@ static int msa_group(int device, poasta_graph **graphs, const char *const *fasta
 int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *fasta, const size_t *fasta_len,
                           uint32_t n_families, const poasta_params *params, uint32_t *scores_out, uint64_t *cells_out) {
     if (!graphs || !fasta || !fasta_len || !params) return POASTA_ERR_INVALID_ARG;
+    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
     tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    if (params->tiebreak == 0) {
+        // reference-exact builds run entirely on the device (msa_engine.cuh): sequences in, finished graphs out
+        DeviceContext &c = ctx_for(device);
+        int rc = c.init(device);
+        if (rc) return rc;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned host_threads = std::min(16u, hw);
+        if (const char *e = getenv("POASTA_HOST_THREADS")) host_threads = std::max(1, atoi(e));
+        std::vector<std::vector<FastaRecord>> recs(n_families);
+        {
+            std::atomic<uint32_t> cursor{0};
+            auto parse = [&]() {
+                for (;;) {
+                    const uint32_t f = cursor.fetch_add(1);
+                    if (f >= n_families) break;
+                    recs[f] = parse_fasta(fasta[f], fasta_len[f]);
+                }
+            };
+            if (n_families < 64 || host_threads <= 1) {
+                parse();
+            } else {
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < host_threads; ++t) pool.emplace_back(parse);
+                for (auto &t : pool) t.join();
+            }
+        }
+        std::vector<EngineFamilyIn> in(n_families);
+        size_t base = 0;
+        for (uint32_t f = 0; f < n_families; ++f) {
+            in[f] = EngineFamilyIn{graphs[f], &recs[f], scores_out ? scores_out + base : nullptr};
+            base += recs[f].size();
+        }
+        EngineStats st;
+        static EngineBuffers ebs[MAX_DEVICES];
+        rc = msa_engine_run(c, ebs[device], in, *params, st, host_threads);
+        tl_search_ms = st.kernel_ms, tl_lane_max_ms = st.kernel_ms, tl_launches = st.launches, tl_cells = st.cells;
+        tl_engine_counts[0] = st.queued, tl_engine_counts[1] = st.visited, tl_engine_counts[2] = st.pruned;
+        if (cells_out) *cells_out = st.cells;
+        return rc;
+    }
     std::vector<size_t> score_base(n_families + 1, 0);
     for (uint32_t f = 0; f < n_families; ++f) {
         size_t n = 0;

@@ -62,7 +62,7 @@ namespace poasta { namespace replay {
 enum { C_POP_M, C_POP_D, C_POP_I, C_POP_STALE, C_DFA_STEP, C_DFA_MATCH, C_DFA_MISMATCH, C_DFA_RELAX_FAIL, C_PRUNE_CALL, C_PRUNE_BUB,
        C_PRUNE_NOREACH, C_PRUNE_PROBE, C_PRUNE_SCORE, C_PUSH, C_RELAX, C_RELAX_OK, C_WINDOW_MOVE, C_POP_SCAN,
        C_NEXT_SAME_STACK, C_NEXT_JUST_PUSHED, C_NEXT_OTHER,
-       C_SPEC_BATCH, C_SPEC_ITEMS, C_SPEC_REUSED, C_SPEC_REUSED_PRUNED, C_SPEC_EPOCH_MISS, C_SPEC_ORDER_MISS, C_SPEC_WRONG, C_N };
+       C_N };
 inline uint64_t rp_counters[C_N];
 } }
 #define RP_CNT(x) (++::poasta::replay::rp_counters[::poasta::replay::x])
@@ -72,16 +72,6 @@ inline uint64_t rp_counters[C_N];
 #define RP_STAT(...)
 #endif
 
-// Bucket-parallel evaluation: compiled into the device code only with -DRP_COOP (NOT the default build
-// of round 1: the protocol below is validated on the host, the device mapping has not run on a GPU yet), and into the host
-// counting build, where the "lanes" are a plain loop.
-#if defined(RP_COOP) || (defined(RP_COUNT) && !defined(__CUDA_ARCH__))
-#define RP_COOP_ON 1
-#define RP_COOPX(...) __VA_ARGS__
-#else
-#define RP_COOPX(...)
-#endif
-
 namespace poasta {
 namespace replay {
 
@@ -89,14 +79,16 @@ constexpr uint32_t UNV = 0xFFFFFFFFu;  // Score::Unvisited
 enum : uint32_t { ST_M = 0, ST_D = 1, ST_I = 2 };
 enum : int { RP_OK = 0, RP_EMPTY_QUEUE = 1, RP_NO_BACKTRACE = 2, RP_SCORE_WRAP = 3, RP_OUT_OF_BLOCKS = 4, RP_OUT_OF_ITEMS = 5,
              RP_PRIORITY_RANGE = 6, RP_OUT_OF_PAIRS = 7 };
-// Visited-table layout: one record {Match, Deletion, Insertion, pad} per (node, offset). A popped state and the states it
-// relaxes mostly share (node, offset) or sit at the neighbouring offset, so they share a 32-byte sector, where three
-// separate planes cost one miss each. -DRP_PLANAR keeps the three-plane layout for A/B measurements.
-#if defined(RP_PLANAR)
-constexpr uint32_t CELL_SLOTS = 3, CELL_STRIDE = 1;
-#else
-constexpr uint32_t CELL_SLOTS = 4, CELL_STRIDE = 4;
-#endif
+// Visited-table layout: one record {Match, Deletion, Insertion, epoch} per (node, offset), read and written as ONE 64-bit
+// (16-bit cells) or 128-bit (32-bit cells) access. A popped state and the states it relaxes mostly share (node, offset) or
+// sit at the neighbouring offset, so they share a 32-byte sector. The fourth slot is the EPOCH of the alignment that wrote
+// the record: a record whose epoch is not the current one reads as "unvisited", so a worker never resets its V x W table
+// between alignments (round 1 spent 66 % of the kernel's DRAM traffic on that reset; the reference's table is sparse for the
+// same reason, gap_affine.rs:442-466). The worker's epoch counter lives in its slab header; the table is zeroed when the
+// counter wraps or the slab is (re)allocated.
+template <typename CellT> struct alignas(4 * sizeof(CellT)) Rec {
+    CellT m, d, i, ep;
+};
 constexpr uint32_t QWIN = 64;  // priorities whose stack heads are kept in the fast window
 
 struct alignas(16) NodeA {
@@ -130,14 +122,14 @@ struct alignas(16) Item {
 };
 
 struct Scratch {  // one slab per in-flight alignment
-    void *planes;          // V * W records of CELL_SLOTS cells {M, D, I, pad}; cell = score | reached-flag (top bit); all-ones-but-top = unvisited
+    void *planes;          // V * W records Rec<CellT> {M, D, I, epoch}; cell = score | reached-flag (top bit, Match only); all-ones-but-top = unvisited
+    uint32_t epoch;        // epoch of this alignment (1 .. CellT max); records stamped otherwise read as unvisited
     uint32_t *qhead;       // f_max * 3 stack heads (0 = empty, else item index + 1) - authoritative outside the window
     uint32_t *qwin;        // QWIN * 3 heads of priorities [win_base, win_base + QWIN): shared memory on the device
     Item *items;           // max_items
     uint32_t *free_slots;  // max_items: stack of recycled item slots (its top stays cache-hot, unlike a list threaded through items)
     uint32_t *rb;          // per node [lo, hi + 1] of the reached offsets (hi + 1 == 0: none)
     uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
-    uint64_t plane_elems;  // V * W (records)
     uint32_t W, max_items, f_max;
 };
 
@@ -152,17 +144,6 @@ struct Result {
     uint32_t n_pairs;  // pairs are written BACKWARDS from out_r[cap-1]; the alignment is out_r[cap-n .. cap)
     int status;
     uint32_t num_queued, num_visited, num_pruned;
-};
-
-// One batch of the bucket-parallel evaluation: the top items of the stack being popped, one per lane, with the outcome of
-// the read-only half of their visit (the prune test) and what that outcome depended on. Shared memory on the device.
-constexpr uint32_t COOP_LANES = 32, COOP_EXITS = 4;
-struct CoopBatch {
-    uint32_t cmd;    // device: 0 idle, 1 evaluate, 2 worker finished (written by lane 0, read by the helper lanes)
-    uint32_t n, st, f;  // items in the batch; state type and priority of the stack they came from
-    uint32_t slot[COOP_LANES], node[COOP_LANES], off[COOP_LANES], score[COOP_LANES];
-    uint32_t pruned[COOP_LANES], n_exit[COOP_LANES];              // n_exit > COOP_EXITS: never reused
-    uint32_t exit[COOP_LANES][COOP_EXITS], epoch[COOP_LANES][COOP_EXITS];  // enclosing bubbles' exits and their epochs at evaluation
 };
 
 template <typename CellT> struct CellTraits;
@@ -181,9 +162,10 @@ template <> struct CellTraits<uint32_t> {
 // Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped (the reference would panic).
 template <typename CellT>
 struct PruneCtx {
-    const CellT *m_plane;  // the visited table; Match cell of (node, off) at (node * W + off) * CELL_STRIDE
-    const uint32_t *rb;    // reached bounds per node
+    const Rec<CellT> *table;  // the visited table; record of (node, off) at node * W + off
+    const uint32_t *rb;       // reached bounds per node
     uint32_t W, Q, o, e;
+    CellT epoch;
 };
 
 // can_improve_bubble for one bubble; true = the state can still improve on it (no prune from this bubble)
@@ -200,10 +182,11 @@ RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, 
     }
     auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
     const uint32_t tmin = off + b.min_d, tmax = off + b.max_d;
-    const CellT *mrow = c.m_plane + (size_t)b.exit * c.W * CELL_STRIDE;
+    const Rec<CellT> *mrow = c.table + (size_t)b.exit * c.W;
     auto at = [&](uint32_t i) -> CellT {  // Match cell of the exit row
         RP_CNT(C_PRUNE_PROBE);
-        return mrow[i * CELL_STRIDE];
+        const Rec<CellT> r = mrow[i];
+        return r.ep == c.epoch ? r.m : CUNV;
     };
     // reached offsets = Match cells of the exit row with the flag bit; scans stay inside [lo, hi]
     auto prev_of = [&](uint32_t lim) -> uint32_t {  // largest reached offset < lim
@@ -300,97 +283,11 @@ struct Search {
     Scratch &s;
     uint32_t n_items = 0, n_free = 0;  // bump pointer into the item arena; height of the recycled-slot stack
     uint32_t f_cur = 0, f_hi = 0, win_base = 0;
+    uint32_t f_top = 0;  // highest priority queued so far: the next alignment of this worker clears qhead[0 .. f_top]
     bool q_empty = true;
     int err = RP_OK;
     // counting builds: how predictable is the next pop? (the item below the popped one / an item queued since / anything else)
     RP_STAT(uint32_t stat_below = 0; uint32_t stat_pushes_at_pop = 0; uint32_t stat_pushes = 0;)
-    // ---- bucket-parallel evaluation -------------------------------------------------------------------
-    // The prune test of the top coop_K items of the stack being popped is evaluated by coop_K lanes at once (device: the
-    // helper lanes of the warp; host: a loop); lane 0, which alone changes state, commits the items in the reference's
-    // order and reuses a result only if (a) the item comes off the stack in the predicted order - pops from other stacks
-    // in between leave the batch alone - and (b) none of its bubbles' exits had a reached mark or a reached score changed
-    // since (exit_epoch). tests/test_replay_core_host.py checks every reused result against a fresh evaluation.
-    RP_COOPX(CoopBatch *coop = nullptr;      // nullptr: disabled
-             uint32_t *exit_epoch = nullptr; // per node, zeroed per alignment
-             uint32_t coop_K = 0, coop_i = 0;
-             int cur_spec = -1;)             // batch index of the item just popped, -1 = evaluate normally
-#if defined(RP_COOP_ON)
-    RP_HD bool prune_pure(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) const {
-        const uint32_t nb = a.counts >> 16;
-        if (nb == 0) return false;
-        const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
-        return prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score) == 1;
-    }
-    // what lane l does in the parallel phase: read-only on the alignment's state, writes only its own batch entries
-    RP_HD void coop_eval_lane(uint32_t l) const {
-        CoopBatch &b = *coop;
-        if (l >= b.n) return;
-        const Item it = s.items[b.slot[l]];
-        const NodeA a = node_a(it.node);
-        const uint32_t nb = a.counts >> 16;
-        b.node[l] = it.node, b.off[l] = it.offset, b.score[l] = it.score;
-        b.n_exit[l] = nb;
-        for (uint32_t k = 0; k < nb && k < COOP_EXITS; ++k) {
-            const uint32_t x = g.bub[a.bub_off + k].exit;
-            b.exit[l][k] = x, b.epoch[l][k] = exit_epoch[x];
-        }
-        b.pruned[l] = prune_pure(it.score, it.node, a, it.offset, b.st) ? 1u : 0u;
-    }
-    RP_HD void coop_phase() {
-#if defined(__CUDA_ARCH__)
-        *(volatile uint32_t *)&coop->cmd = 1;
-        __syncwarp();  // releases the helper lanes (replay_kernel.cuh), which see the batch written above
-        coop_eval_lane(0);
-        __syncwarp();  // their results are visible from here on
-#else
-        for (uint32_t l = 0; l < coop->n; ++l) coop_eval_lane(l);
-#endif
-    }
-    RP_HD void coop_on_pop(uint32_t slot, uint32_t st, uint32_t f) {
-        cur_spec = -1;
-        if (!coop || !coop_K) return;
-        CoopBatch &b = *coop;
-        if (coop_i < b.n && b.slot[coop_i] == slot) {
-            cur_spec = (int)coop_i++;
-            return;
-        }
-        // a pop from another stack (e.g. the Match state a popped gap state just closed into) leaves the batch alone:
-        // lane 0 handles that state on its own and comes back to the batch's stack afterwards
-        if (coop_i < b.n && (f != b.f || st != b.st)) return;
-        if (coop_i < b.n) RP_CNT(C_SPEC_ORDER_MISS);
-        b.f = f, b.st = st;
-        uint32_t n = 0;
-        for (uint32_t sl = slot;;) {  // lanes 0..K-1 take the items from the top of this stack downwards
-            b.slot[n++] = sl;
-            const uint32_t next = s.items[sl].next;
-            if (n >= coop_K || n >= COOP_LANES || !next) break;
-            sl = next - 1;
-        }
-        b.n = n;
-        coop_i = 0;
-        coop_phase();
-        RP_CNT(C_SPEC_BATCH);
-        RP_STAT(rp_counters[C_SPEC_ITEMS] += n;)
-        cur_spec = (int)coop_i++;
-    }
-    // result of the batch entry of the state just popped if it is still valid, else -1
-    RP_HD int coop_lookup(uint32_t score, uint32_t node, uint32_t off, uint32_t st) {
-        if (cur_spec < 0) return -1;
-        const CoopBatch &b = *coop;
-        const uint32_t l = (uint32_t)cur_spec;
-        cur_spec = -1;
-        if (b.node[l] != node || b.off[l] != off || b.st != st || b.score[l] != score) return -1;
-        bool fresh = b.n_exit[l] <= COOP_EXITS;
-        for (uint32_t k = 0; k < b.n_exit[l] && k < COOP_EXITS; ++k) fresh = fresh && exit_epoch[b.exit[l][k]] == b.epoch[l][k];
-        if (!fresh) {
-            RP_CNT(C_SPEC_EPOCH_MISS);
-            return -1;
-        }
-        RP_CNT(C_SPEC_REUSED);
-        if (b.pruned[l]) RP_CNT(C_SPEC_REUSED_PRUNED);
-        return (int)b.pruned[l];
-    }
-#endif
 #if defined(RP_PROFILE)
     long long prof_prune = 0, prof_push = 0, prof_pop = 0;
     uint32_t prof_n_prune = 0;
@@ -403,51 +300,51 @@ struct Search {
     RP_HD bool sym_eq(uint32_t node, const NodeA &a, uint8_t c) const { return node == g.end || (a.symflags & 0xFF) == c; }
 
     // ---- visited table -------------------------------------------------------------------------
-    RP_HD CellT *cell(uint32_t node, uint32_t off, uint32_t st) const {
-#if defined(RP_PLANAR)
-        return static_cast<CellT *>(s.planes) + (size_t)st * s.plane_elems + (size_t)node * s.W + off;
-#else
-        return static_cast<CellT *>(s.planes) + ((size_t)node * s.W + off) * CELL_STRIDE + st;
-#endif
+    using R = Rec<CellT>;
+    RP_HD R *rec_ptr(uint32_t node, uint32_t off) const { return static_cast<R *>(s.planes) + (size_t)node * s.W + off; }
+    // one vector load; a record of another epoch reads as three unvisited cells (stamped with the current epoch, so that
+    // storing it back after changing one cell makes the whole record current)
+    RP_HD R load(const R *ptr) const {
+        R r = *ptr;
+        if (r.ep != (CellT)s.epoch) r = R{CUNV, CUNV, CUNV, (CellT)s.epoch};
+        return r;
+    }
+    RP_HD static CellT field(const R &r, uint32_t st) { return st == ST_M ? r.m : (st == ST_D ? r.d : r.i); }
+    RP_HD static void set_field(R &r, uint32_t st, CellT v) {
+        if (st == ST_M) r.m = v;
+        else if (st == ST_D) r.d = v;
+        else r.i = v;
     }
     RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
-        const CellT v = (CellT)(*cell(node, off, st) & (CellT)~FLAG);
+        const CellT v = (CellT)(field(load(rec_ptr(node, off)), st) & (CellT)~FLAG);
         return v == CUNV ? UNV : (uint32_t)v;
     }
-    RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) { *cell(node, off, st) = (CellT)v; }
-    RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {  // update_score_if_lower (strict)
+    RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
+        R *ptr = rec_ptr(node, off);
+        R r = load(ptr);
+        set_field(r, st, (CellT)v);
+        *ptr = r;
+    }
+    // update_score_if_lower (strict) on a record loaded earlier (together with other loads) and not written since
+    RP_HD bool relax_loaded(R *ptr, R r, uint32_t st, uint32_t v) {
         if (CHECK_WRAP && v >= (uint32_t)CUNV) {  // cannot happen when the host sized CellT correctly
             err = RP_SCORE_WRAP;
             return false;
         }
-        CellT *c = cell(node, off, st);
-        const CellT cur = *c;
+        const CellT cur = field(r, st);
         const CellT curv = (CellT)(cur & (CellT)~FLAG);
         RP_CNT(C_RELAX);
         if (curv == CUNV || v < (uint32_t)curv) {
             RP_CNT(C_RELAX_OK);
-            RP_COOPX(if ((cur & FLAG) && exit_epoch) ++exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
-            *c = (CellT)((CellT)v | (CellT)(cur & FLAG));  // a reached offset stays reached when its score improves
+            set_field(r, st, (CellT)((CellT)v | (CellT)(cur & FLAG)));  // a reached offset stays reached when its score improves
+            *ptr = r;
             return true;
         }
         return false;
     }
-
-    // relax() on a cell whose current value `cur` was loaded earlier (together with other loads) and not written since
-    RP_HD bool relax_loaded(CellT *c, CellT cur, uint32_t v) {
-        if (CHECK_WRAP && v >= (uint32_t)CUNV) {
-            err = RP_SCORE_WRAP;
-            return false;
-        }
-        const CellT curv = (CellT)(cur & (CellT)~FLAG);
-        RP_CNT(C_RELAX);
-        if (curv == CUNV || v < (uint32_t)curv) {
-            RP_CNT(C_RELAX_OK);
-            RP_COOPX(if ((cur & FLAG) && exit_epoch) ++exit_epoch[(size_t)(c - static_cast<CellT *>(s.planes)) / CELL_STRIDE / s.W];)
-            *c = (CellT)((CellT)v | (CellT)(cur & FLAG));
-            return true;
-        }
-        return false;
+    RP_HD bool relax(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
+        R *ptr = rec_ptr(node, off);
+        return relax_loaded(ptr, load(ptr), st, v);
     }
 
     // ---- score arithmetic with the reference's NonMaxU32 / wrapping behaviour -------------------------
@@ -526,6 +423,7 @@ struct Search {
             }
             slot = n_items++;
         }
+        if (f > f_top) f_top = f;
         uint32_t *head = head_ptr(f) + st;
         s.items[slot] = Item{score, node, off, *head};
         *head = slot + 1;
@@ -548,7 +446,6 @@ struct Search {
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
-                    RP_COOPX(coop_on_pop(slot, k, f_cur);)
                     RP_STAT(if (slot + 1 == stat_below) RP_CNT(C_NEXT_SAME_STACK);
                             else if (stat_pushes != stat_pushes_at_pop) RP_CNT(C_NEXT_JUST_PUSHED);  // approximation: something was queued since
                             else RP_CNT(C_NEXT_OTHER);
@@ -570,8 +467,10 @@ struct Search {
     // ---- reached marks (BTreeSet<offset> per exit; gap_affine.rs:767-773) -------------------------------
     RP_HD void mark_reached(uint32_t node, bool is_exit, uint32_t off, uint32_t st) {
         if (st == ST_M && is_exit) {
-            RP_COOPX(if (exit_epoch) ++exit_epoch[node];)
-            *cell(node, off, ST_M) |= FLAG;
+            R *ptr = rec_ptr(node, off);
+            R r = load(ptr);
+            r.m |= FLAG;
+            *ptr = r;
             uint32_t *b = s.rb + 2 * (size_t)node;
             if (b[1] == 0) {
                 b[0] = off, b[1] = off + 1;
@@ -583,18 +482,11 @@ struct Search {
     }
 
     RP_HD bool prune(uint32_t score, uint32_t node, const NodeA &a, uint32_t off, uint32_t st) {  // gap_affine.rs:780-792
-        RP_COOPX({
-            const int hit = coop_lookup(score, node, off, st);
-            if (hit >= 0) {
-                RP_STAT(if (prune_pure(score, node, a, off, st) != (hit == 1)) RP_CNT(C_SPEC_WRONG);)
-                return hit == 1;
-            }
-        })
         const uint32_t nb = a.counts >> 16;
         if (nb == 0) return false;
         RP_T0;
         RP_CNT(C_PRUNE_CALL);
-        const PruneCtx<CellT> c{static_cast<const CellT *>(s.planes), s.rb, s.W, Q, p.o, p.e};
+        const PruneCtx<CellT> c{static_cast<const R *>(s.planes), s.rb, s.W, Q, p.o, p.e, (CellT)s.epoch};
         const int r = prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
         RP_ACC(prof_prune);
@@ -685,7 +577,7 @@ struct Search {
                 break;
             }
             // the state's own cell (stale test) and its node record, issued as one group of loads
-            const CellT own = *cell(it.node, it.offset, st);
+            const CellT own = field(load(rec_ptr(it.node, it.offset)), st);
             const NodeA na = node_a(it.node);
             const NodeB nb = node_b(it.node);
             const uint32_t n_succ = na.counts & 0xFFFF;
@@ -770,13 +662,13 @@ struct Search {
                                 break;
                             }
                             // the child's cell and its record in one group of loads
-                            CellT *cc = cell(child, po + 1, ST_M);
-                            const CellT ccur = *cc;
+                            R *cc = rec_ptr(child, po + 1);
+                            const R ccur = load(cc);
                             ca = node_a(child);
                             cb = node_b(child);
                             RP_CNT(C_DFA_STEP);
                             if ((ca.symflags & 0xFF) == q[po]) {
-                                if (relax_loaded(cc, ccur, score)) {
+                                if (relax_loaded(cc, ccur, ST_M, score)) {
                                     RP_CNT(C_DFA_MATCH);
                                     kind = 3, cn = child, co = po + 1;
                                     break;
@@ -837,10 +729,10 @@ struct Search {
                     } else {
                         break;
                     }
-                    CellT *cc = cell(n_, o_, s_);
-                    const CellT ccur = *cc;
+                    R *cc = rec_ptr(n_, o_);
+                    const R ccur = load(cc);
                     const NodeB b = node_b(n_);  // loaded with the cell, used only when the relaxation succeeds
-                    if (relax_loaded(cc, ccur, v_)) {
+                    if (relax_loaded(cc, ccur, s_, v_)) {
                         push(n_, b.dist_min, b.dist_max, o_, s_, qv_);
                         ++res.num_queued;
                     }

@@ -1,9 +1,11 @@
 // Device launcher for the order-exact search (replay_core.hpp). Included by align.cu.
 //
-// One warp = one in-flight alignment ("worker"). All 32 lanes zero the worker's scratch slab with
-// 128-bit stores, then lane 0 runs the (inherently sequential) state machine. Workers pull
-// alignments from a global counter, so a launch keeps every SM's warp slots busy until the batch
-// is drained. Results go to the same staging / scan / compact path as the DP traceback.
+// One warp = one in-flight alignment ("worker"). The worker's V x W visited table is never reset:
+// its records carry the epoch of the alignment that wrote them (replay_core.hpp Rec), so the 32 lanes
+// only clear the bucket heads and reached bounds the previous alignment touched; then lane 0 runs the
+// (inherently sequential) state machine. Workers pull alignments from a global counter, so a launch
+// keeps every SM's warp slots busy until the batch is drained. Results go to the same staging / scan /
+// compact path as the DP traceback. (Progressive builds use the persistent engine in msa_engine.cuh.)
 #pragma once
 #include "replay_core.hpp"
 #include "search_index.hpp"
@@ -26,10 +28,7 @@ struct ReplayDev {
     uint32_t n_alns;
     replay::Params prm;
     uint8_t *slabs;
-    uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_dfa;  // byte offsets inside a slab (score planes at 0)
-#if defined(RP_COOP)
-    uint64_t off_epoch;  // per-node epochs of the bucket-parallel evaluation (replay_core.hpp)
-#endif
+    uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_dfa;  // byte offsets inside a slab (header at 0, records at SLAB_CELLS)
     uint32_t max_items;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
@@ -38,14 +37,52 @@ struct ReplayDev {
 
 constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few workers over all SMs; 2 reaches 64 warps/SM
 
+// Slab header (first 256 bytes of a worker's slab; the visited table starts at SLAB_CELLS). The slab buffer is zeroed by the
+// host when it is (re)allocated or its layout changes, so epoch 0 means "never written".
+constexpr uint64_t SLAB_CELLS = 256;
+struct SlabHeader {
+    uint32_t epoch;    // epoch of the last alignment this worker ran
+    uint32_t dirty_f;  // priorities [0, dirty_f) of qhead may be non-zero
+};
+template <typename CellT> struct EpochTraits;
+template <> struct EpochTraits<uint16_t> { static constexpr uint32_t MAX = 0xFFFEu; };
+template <> struct EpochTraits<uint32_t> { static constexpr uint32_t MAX = 0xFFFFFFFEu; };
+
+// Start of one alignment on a worker, all 32 lanes: next epoch (zeroing the table only when the counter wraps), bucket
+// heads of the priorities the previous alignment touched, reached bounds of this graph's nodes, the queue window.
+// Returns the epoch (warp-uniform).
+template <typename CellT>
+__device__ __forceinline__ uint32_t worker_begin_alignment(uint8_t *slab, uint64_t cell_bytes, uint64_t off_qhead, uint64_t off_rb, uint32_t V,
+                                                           uint32_t *s_qwin, uint32_t lane) {
+    SlabHeader *hdr = reinterpret_cast<SlabHeader *>(slab);
+    uint32_t ep = hdr->epoch + 1, dirty = hdr->dirty_f;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (ep > EpochTraits<CellT>::MAX) {
+        uint4 *p0 = reinterpret_cast<uint4 *>(slab + SLAB_CELLS);
+        for (uint64_t i = lane; i < cell_bytes / 16; i += 32) p0[i] = z;
+        ep = 1;
+    }
+    uint4 *p1 = reinterpret_cast<uint4 *>(slab + off_qhead);
+    const uint32_t n1 = (uint32_t)(((uint64_t)dirty * 3 + 3) / 4);
+    for (uint32_t i = lane; i < n1; i += 32) p1[i] = z;
+    uint4 *p2 = reinterpret_cast<uint4 *>(slab + off_rb);
+    const uint32_t n2 = (uint32_t)(((uint64_t)V * 2 + 3) / 4);
+    for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
+    for (uint32_t i = lane; i < replay::QWIN * 3; i += 32) s_qwin[i] = 0;
+    __syncwarp();
+    return ep;
+}
+__device__ __forceinline__ void worker_end_alignment(uint8_t *slab, uint32_t epoch, uint32_t f_top) {
+    SlabHeader *hdr = reinterpret_cast<SlabHeader *>(slab);
+    hdr->epoch = epoch;
+    hdr->dirty_f = f_top + 1;
+}
+
 // MINB = minimum resident CTAs per SM the register allocation must allow. Only lane 0 of a warp runs the state machine
 // but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
 template <typename CellT, int MINB, int HEUR>
 __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
     __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];  // queue-head window of each worker
-#if defined(RP_COOP)
-    __shared__ replay::CoopBatch s_coop[REPLAY_MAX_WARPS_PER_CTA];  // batch of the bucket-parallel evaluation of each worker
-#endif
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
@@ -57,35 +94,8 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
         const AlnDesc ad = B.alns[a];
         const RGraphDesc gd = B.graphs[ad.graph];
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
-        // reset the slab for THIS alignment with 128-bit stores: score planes to "unvisited", bucket heads and reached bounds to 0
-        {
-            const uint32_t pat = sizeof(CellT) == 2 ? 0x7FFF7FFFu : 0x7FFFFFFFu;
-            const uint4 unv = make_uint4(pat, pat, pat, pat), z = make_uint4(0, 0, 0, 0);
-            uint4 *p0 = reinterpret_cast<uint4 *>(slab);
-            const uint64_t n0 = ((uint64_t)replay::CELL_SLOTS * gd.V * dims.W * sizeof(CellT) + 15) / 16;
-            for (uint64_t i = lane; i < n0; i += 32) p0[i] = unv;
-            uint4 *p1 = reinterpret_cast<uint4 *>(slab + B.off_qhead);
-            const uint32_t n1 = ((uint64_t)dims.f_max * 3 + 3) / 4;
-            for (uint32_t i = lane; i < n1; i += 32) p1[i] = z;
-            uint4 *p2 = reinterpret_cast<uint4 *>(slab + B.off_rb);
-            const uint32_t n2 = ((uint64_t)gd.V * 2 + 3) / 4;
-            for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
-            for (uint32_t i = lane; i < replay::QWIN * 3; i += 32) s_qwin[wib][i] = 0;
-#if defined(RP_COOP)
-            uint4 *p3 = reinterpret_cast<uint4 *>(slab + B.off_epoch);
-            const uint32_t n3 = ((uint64_t)gd.V + 3) / 4;
-            for (uint32_t i = lane; i < n3; i += 32) p3[i] = z;
-            if (lane == 0) s_coop[wib].cmd = 0, s_coop[wib].n = 0;
-#endif
-        }
-        __syncwarp();
-#if defined(RP_COOP)
-        // every lane holds the (read-only) view of the alignment; lane 0 runs the state machine, lanes 1..31 wait for batches
-        constexpr bool all_lanes = true;
-#else
-        constexpr bool all_lanes = false;
-#endif
-        if (lane == 0 || all_lanes) {
+        const uint32_t epoch = worker_begin_alignment<CellT>(slab, B.off_qhead - SLAB_CELLS, B.off_qhead, B.off_rb, gd.V, s_qwin[wib], lane);
+        if (lane == 0) {
             replay::Graph g;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
             g.nodes = B.nodes + gd.node_base;
@@ -95,8 +105,8 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             g.path_off = B.path_off + gd.pathoff_base;
             g.path_rem = B.path_rem + gd.path_base;
             replay::Scratch s;
-            s.planes = slab;
-            s.plane_elems = (uint64_t)gd.V * dims.W;
+            s.planes = slab + SLAB_CELLS;
+            s.epoch = epoch;
             s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
             s.qwin = s_qwin[wib];
             s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
@@ -109,22 +119,8 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             const long long t_begin = clock64();
 #endif
             replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
-#if defined(RP_COOP)
-            search.coop = &s_coop[wib];
-            search.exit_epoch = reinterpret_cast<uint32_t *>(slab + B.off_epoch);
-            search.coop_K = replay::COOP_LANES;
-            if (lane != 0) {
-                // helper lane: one evaluation per batch lane 0 announces (two __syncwarp per batch on both sides,
-                // replay_core.hpp coop_phase), until lane 0 reports the end of the alignment
-                for (;;) {
-                    __syncwarp();
-                    if (*(volatile uint32_t *)&s_coop[wib].cmd == 2) break;
-                    search.coop_eval_lane(lane);
-                    __syncwarp();
-                }
-            } else {
-#endif
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
+            worker_end_alignment(slab, epoch, search.f_top);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;
             B.status[a] = r.status;
@@ -138,11 +134,6 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
                            a, total, search.prof_prune, 100.0 * search.prof_prune / total, search.prof_n_prune,
                            search.prof_prune / (search.prof_n_prune ? search.prof_n_prune : 1), search.prof_push,
                            100.0 * search.prof_push / total, r.num_visited, r.num_queued, r.num_pruned, total / (r.num_visited ? r.num_visited : 1));
-            }
-#endif
-#if defined(RP_COOP)
-            *(volatile uint32_t *)&s_coop[wib].cmd = 2;
-            __syncwarp();  // releases the helper lanes for the last time
             }
 #endif
         }

@@ -61,22 +61,16 @@ def _counters():
     return list(buf)[:n]
 
 
-@pytest.mark.parametrize("K", [8, 32])
-def test_bucket_parallel_evaluation_model(K, monkeypatch):
-    """Design model for the device: the prune test of the top K items of the stack being popped is
-    evaluated ahead ("K lanes at once") and reused by the sequential committer when no reached mark or reached score of
-    the bubbles' exits changed in between and the items come off in the predicted order. Results and counters must stay
-    identical to the oracle, no reused result may differ from a fresh evaluation, and most pop-site tests are covered."""
-    monkeypatch.setenv("RP_SPEC_K", str(K))
-    _counters()
+@pytest.mark.parametrize("epoch", [2, 0x7FFF, 0xFFFE])
+def test_stale_records_read_as_unvisited(epoch, monkeypatch):
+    """The visited table is never reset between alignments: records carry the epoch of the alignment that wrote them and any
+    other epoch reads as unvisited (replay_core.hpp Rec). The hook pre-fills the table with garbage records of OTHER epochs;
+    results and counters must stay identical to the oracle, with 16-bit and 32-bit cells."""
+    monkeypatch.setenv("RP_HOST_EPOCH", str(epoch))
     n = 0
-    for f in (0, 2):
-        for g, seq, st, sc, pairs, stats in _cases(synth.config2_family(f, n_seqs=7, root_len=300, rate=0.06), 1):
-            st2, sc2, pairs2, stats2 = H.replay_host_align(g, seq, cell16=True)
+    for g, seq, st, sc, pairs, stats in _cases(synth.config2_family(1, n_seqs=6, root_len=250, rate=0.06), 1):
+        for cell16 in (True, False):
+            st2, sc2, pairs2, stats2 = H.replay_host_align(g, seq, cell16=cell16)
             assert (st2, sc2, pairs2, stats2[:3]) == (st, sc, pairs, stats[:3])
-            n += 1
-    c = _counters()
-    batches, items, reused, _, epoch_miss, order_miss, wrong = c[-7:]
-    assert n == 12 and wrong == 0 and batches > 0
-    assert reused > 10 * (epoch_miss + order_miss)   # the per-exit validation rarely fails
-    assert reused / batches > (3 if K == 8 else 5)   # several committed states per parallel evaluation
+        n += 1
+    assert n == 5

@@ -9,8 +9,7 @@ from poasta_b200 import POAGraph, synth  # noqa: E402
 
 NAMES = ["pop_M", "pop_D", "pop_I", "pop_stale", "dfa_step", "dfa_match", "dfa_mismatch", "dfa_relax_fail", "prune_call", "prune_bub",
          "prune_noreach", "prune_probe", "prune_score", "push", "relax", "relax_ok", "window_move", "pop_scan",
-         "next_same_stack", "next_just_pushed", "next_other",
-         "spec_batches", "spec_items", "spec_reused", "spec_reused_pruned", "spec_epoch_miss", "spec_order_miss", "spec_wrong"]
+         "next_same_stack", "next_just_pushed", "next_other"]
 
 
 def counters():
