@@ -1,26 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric (GCUPS, sequences/s) on config 2 (gene families, 20 x 1 kb, 5% edits).
+"""bench.py — BASELINE.json's metric (GCUPS, sequences/s) on the reference's configs; default = config 2 (gene families,
+20 x 1 kb, 5 % edits), the configuration the metric is quoted on.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--families F] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--families F] [--impl ours|reference]
 
-One "step" = one progressive-MSA pass of the hot path over one batch of F families (19 alignment rounds,
-each round one device batch), called through the public C-ABI entry `poasta_msa_batch` with HOST buffers.
-Step k aligns families [k*F, (k+1)*F) with F = 5,000 by default: the default 2 steps are BASELINE.json's config 2
-(10,000 families); warm-up steps use further families of the same shape.
-  value   GCUPS over the device kernels only (CUDA events on the launching streams around the DP fill /
-          traceback and the order-exact search launches; inputs of each launch resident in HBM). The pipeline
-          lanes of a rank run their kernels concurrently, so the device time of a step is the largest per-lane
-          sum of kernel time (the device-side critical path), not the sum over lanes;
-  e2e     GCUPS of the whole call: FASTA text in host memory -> final graphs, including flattening,
-          H2D/D2H copies and the host-side graph insertion between rounds — the headline.
---tiebreak exact (default) returns the reference's alignments bit for bit (DP score + order-exact search);
---tiebreak dp returns the optimal score and a co-optimal alignment from the DP traceback alone.
-1 CU = the three states (M, I, D) of one (real node, query position) pair; cells = sum V_real * Q
-(SURVEY.md §8d). Under torchrun each rank takes a disjoint shard of families (no collective on the
-data path; weak scaling: F families per GPU).
+One "step" = one pass of the hot path over one batch of synthetic input through the public C-ABI entry with HOST buffers:
+  config 2/3/4  `poasta_msa_batch`: progressive MSA of F families (FASTA text in host memory -> final graphs in host memory).
+                In reference-exact mode (default) the whole build runs on the device: sequences in, ONE persistent kernel per
+                batch (per-round graph index, order-exact search, graph update, all on the GPU), finished graphs out.
+  config 5      `poasta_align_batch`: R reads against one fixed graph, ends-free, -H path (library semantics).
+  value   GCUPS over the device kernels only (CUDA events on the launching stream around the engine / search launches; the
+          step's inputs are resident in HBM when they start);
+  e2e     GCUPS of the whole call with host buffers, H2D / D2H copies and the host-side conversion of the results inside
+          the timed region — the headline.
+1 CU = the three states (M, I, D) of one (real node, query position) pair; cells = sum V_real * Q.
+Under torchrun each rank takes a disjoint shard of the units (no collective on the data path; weak scaling).
 
---impl reference times the CPU restatement of the reference's A* path (the oracle; the Rust reference
-cannot be built in this image) on all host cores, one family per task, on a bounded sample.
+--impl reference times the CPU restatement of the reference's A* path (oracle/; the Rust reference cannot be built in this
+image, so cpu_baseline.kind is "port") on all host cores, one family / read per task, on a bounded sample of every step.
 """
 import argparse
 import ctypes as C
@@ -34,14 +31,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES_PER_CU = 1.0      # SURVEY.md §8d: traceback budget 1 B/CU; scores stay on chip
-ALG_INT_OPS_PER_CU = 12.0   # SURVEY.md §8d: 6*d_v + 6 at in-degree 1
+ALG_BYTES_PER_CU = 1.0      # SURVEY.md 8d: traceback budget 1 B/CU; scores stay on chip
+ALG_INT_OPS_PER_CU = 12.0   # SURVEY.md 8d: 6*d_v + 6 at in-degree 1
 
 
-def measured_traffic():
-    """DRAM bytes per cell update of each kernel from the committed ncu captures (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+def measured_traffic(name):
+    """DRAM bytes per cell update of a kernel from the committed ncu captures (profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    return json.load(open(p)).get(name) if os.path.exists(p) else None
 
 
 def peaks():
@@ -82,13 +79,43 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def make_families(first, count, args):
-    """Families [first, first + count) of config 2 (seeded per family, identical for both bench arms)."""
+# ---- workloads (seeded per unit, identical for both bench arms) ---------------------------------------
+CONFIGS = {
+    2: dict(name="config2", seqs=20, length=1000, rate=0.05, units=5000, unit="families",
+            what="synthetic gene families x 20 seqs x 1 kb, 5% subs+indels, global, costs 4/6/2, mingap; progressive MSA (19 rounds)"),
+    3: dict(name="config3", seqs=30, length=500, rate=0.10, units=12000, unit="windows",
+            what="long-read consensus windows x 30 reads x 500 bp, 10% error, global, costs 4/6/2, mingap; progressive MSA (29 rounds)"),
+    4: dict(name="config4", seqs=40, length=1500, rate=0.15, units=1, unit="family",
+            what="ONE family of 16S-like 1.5 kb sequences at 15% divergence (a single sequential chain: latency-bound, replicas only); "
+                 "bounded to the first `seqs` members of the 1,000"),
+    5: dict(name="config5", seqs=50, length=20000, rate=0.01, units=20000, unit="reads", read_len=2000, read_rate=0.05,
+            what="reads of 2 kb (5% error) against ONE fixed graph of 50 haplotypes x 20 kb (1% divergence), ends-free, -H path, "
+                 "library semantics (every read against the fixed graph)"),
+}
+
+
+def make_units(cfg, first, count, args):
     from poasta_b200 import synth
-    return [synth.config2_family(first + f, n_seqs=args.seqs, root_len=args.length, rate=args.rate) for f in range(count)]
+    c = CONFIGS[cfg]
+    seqs, length, rate = args.seqs or c["seqs"], args.length or c["length"], args.rate if args.rate is not None else c["rate"]
+    if cfg == 2:
+        return [synth.config2_family(first + f, n_seqs=seqs, root_len=length, rate=rate) for f in range(count)]
+    if cfg == 3:
+        return [synth.config3_window(first + f, n_reads=seqs, template_len=length, rate=rate) for f in range(count)]
+    if cfg == 4:
+        return [synth.config4_family(n_seqs=seqs, root_len=length, rate=rate)]
+    raise ValueError(cfg)
 
 
-def cpu_reference(fastas, threads):
+def config5_inputs(args, n_reads, first):
+    """(haplotype FASTA, reads [first, first + n_reads)). The graph is built from the haplotypes once, outside the timed region."""
+    from poasta_b200 import synth
+    c = CONFIGS[5]
+    return synth.config5_reads(args.seqs or c["seqs"], args.length or c["length"], args.rate if args.rate is not None else c["rate"],
+                               first, n_reads, c["read_len"], c["read_rate"])
+
+
+def cpu_reference_msa(fastas, threads, prm=(4, 6, 2, 0, 1)):
     """The CPU arm: oracle (restated reference A*) progressive MSA, one family per task over `threads` threads."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
@@ -96,10 +123,29 @@ def cpu_reference(fastas, threads):
     ptr = (C.c_char_p * n)(*fastas)
     lens = (C.c_size_t * n)(*[len(f) for f in fastas])
     cells, seqs, err = C.c_uint64(), C.c_uint64(), C.c_int()
-    secs = H.oracle().oracle_msa_many(ptr, lens, n, 4, 6, 2, 0, 1, threads, C.byref(cells), C.byref(seqs), C.byref(err))
+    secs = H.oracle().oracle_msa_many(ptr, lens, n, *prm, threads, C.byref(cells), C.byref(seqs), C.byref(err))
     if err.value:
         raise RuntimeError(f"oracle failed: {err.value}")
     return secs, cells.value, seqs.value
+
+
+def cpu_reference_reads(graph, reads, threads):
+    """Config 5 CPU arm: every read against the fixed graph with the oracle, ends-free, -H path, `threads` threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    return H.oracle_align_many(graph, reads, threads, mode=1, heuristic=2)
+
+
+def workload_config(cfg, args, units, world=1):
+    c = CONFIGS[cfg]
+    d = {"workload": f"{c['name']}: {c['what']}; {args.steps} steps of {units} {c['unit']} per GPU",
+         f"{c['unit']}_per_step_per_gpu": units, "tiebreak": getattr(args, "tiebreak", "exact"),
+         "l2": "every step reads different units; the per-alignment working sets (visited tables, graphs) total tens of GB per GPU, "
+               "far larger than the 126 MB L2"}
+    for k in ("seqs", "length", "rate"):
+        if getattr(args, k) is not None:
+            d[k] = getattr(args, k)
+    return d
 
 
 def run_reference(args):
@@ -108,37 +154,67 @@ def run_reference(args):
         return
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     cores = os.cpu_count() or 1
-    sample = max(8, min(args.families, 2 * cores))  # bounded sample of every step's batch (about 5-10 s of CPU work each)
-    for _ in range(1 if args.warmup else 0):
-        cpu_reference(make_families(args.steps * args.families, max(1, cores // 2), args), cores)
+    cfg = args.config
+    units = args.families or CONFIGS[cfg]["units"]
     tot_s = tot_cells = tot_seqs = 0
-    for k in range(args.steps):
-        s, c, q = cpu_reference(make_families(k * args.families, sample, args), cores)
-        tot_s += s
-        tot_cells += c
-        tot_seqs += q
+    if cfg == 5:
+        from poasta_b200 import POAGraph
+        sample = max(8, min(units, 64 * cores))
+        haps, _ = config5_inputs(args, 0, 0)
+        graph = build_config5_graph(haps, device=None)
+        for k in range(args.steps):
+            _, reads = config5_inputs(args, sample, k * units)
+            s, c = cpu_reference_reads(graph, reads, cores)
+            tot_s += s
+            tot_cells += c
+            tot_seqs += len(reads)
+        what = f"first {sample} of the {units} reads of every step, one read per task, {cores} threads"
+    else:
+        sample = max(1, min(units, 2 * cores)) if cfg != 3 else max(1, min(units, 8 * cores))
+        if args.warmup:
+            cpu_reference_msa(make_units(cfg, args.steps * units, max(1, min(sample, cores // 2)), args), cores)
+        for k in range(args.steps):
+            s, c, q = cpu_reference_msa(make_units(cfg, k * units, sample, args), cores)
+            tot_s += s
+            tot_cells += c
+            tot_seqs += q
+        what = f"first {sample} of the {units} {CONFIGS[cfg]['unit']} of every step, one per task, {cores} threads"
     gcups = tot_cells / tot_s / 1e9
     line = {
         "impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "seqs_per_s": tot_seqs / tot_s,
-        "config": workload_config(args, args.families),
+        "config": workload_config(cfg, args, units),
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": "port",
-                         "sample": f"first {sample} of the {args.families} families of every step, one family per task, {cores} threads; "
-                                   "equivalent GCUPS (A* visits a fraction of the cells)"},
+                         "sample": what + "; equivalent GCUPS (A* visits a fraction of the cells); oracle built -O3 -march=native"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, families, world=1):
-    total = families * args.steps * world
-    return {"workload": f"config2: {total} synthetic gene families x {args.seqs} seqs x {args.length} bp, "
-                        f"{args.rate:.0%} subs+indels, global, costs 4/6/2, mingap; progressive MSA ({args.seqs - 1} rounds) in "
-                        f"{args.steps} steps of {families} families per GPU",
-            "families_per_step_per_gpu": families, "tiebreak": getattr(args, "tiebreak", "exact"),
-            "l2": "every step reads different families; per-round working set (tables, trace) is far larger than the 126 MB L2"}
+def build_config5_graph(haps, device):
+    """The fixed graph of config 5. Built once, outside the timed region: on the GPU arm with the DP-only mode of the product
+    (optimal alignments; which co-optimal one is irrelevant for a benchmark input), on the CPU arm with the oracle."""
+    from poasta_b200 import POAGraph
+    cache = os.path.join(ROOT, "gpurun_out", f"config5_graph_{len(haps)}.poasta")
+    if os.path.exists(cache):
+        return POAGraph.load(open(cache, "rb").read())
+    if device is None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        rc, data, _, _ = H.oracle_msa(haps, fmt=3)
+        assert rc == 0
+        g = POAGraph.load(data)
+    else:
+        from poasta_b200 import TIEBREAK_DP, msa_batch
+        g = msa_batch([haps], device=device, tiebreak=TIEBREAK_DP)[0][0]
+    try:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        open(cache, "wb").write(g.save())
+    except OSError:
+        pass
+    return g
 
 
 def main():
@@ -147,11 +223,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "5000")), help="families per step per GPU")
+    ap.add_argument("--config", type=int, default=int(os.environ.get("BENCH_CONFIG", "2")), choices=[2, 3, 4, 5])
+    ap.add_argument("--families", type=int, default=int(os.environ.get("BENCH_FAMILIES", "0")), help="units (families / windows / reads) per step per GPU")
     ap.add_argument("--tiebreak", default=os.environ.get("BENCH_TIEBREAK", "exact"), choices=["exact", "dp"])
-    ap.add_argument("--seqs", type=int, default=20)
-    ap.add_argument("--length", type=int, default=1000)
-    ap.add_argument("--rate", type=float, default=0.05)
+    ap.add_argument("--seqs", type=int, default=None)
+    ap.add_argument("--length", type=int, default=None)
+    ap.add_argument("--rate", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -165,9 +242,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: poasta_b200 has no CPU fallback")
-    # the ranks of one node share its host cores: give every pipeline lane (4 per rank) its share of them
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("POASTA_THREADS_PER_LANE", str(max(1, min(16, (os.cpu_count() or 1) // (local_world * 4)))))
+    cores = os.cpu_count() or 1
+    # the ranks of one node share its host cores (only the FASTA parsing and the final graph conversion run there)
+    os.environ.setdefault("POASTA_HOST_THREADS", str(max(1, min(16, cores // local_world))))
+    os.environ.setdefault("POASTA_THREADS_PER_LANE", str(max(1, min(16, cores // (local_world * 4)))))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -177,27 +256,53 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
-    from poasta_b200 import aligner, msa_batch
-
-    from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT
-    tiebreak = TIEBREAK_DP if args.tiebreak == "dp" else TIEBREAK_EXACT
-    F = args.families
-    # step k of rank r aligns families [(k * world + r) * F, ...); warm-up batches lie beyond the timed ones
+    from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT, AffinePathAware, AlignmentType, aligner, align_batch, msa_batch
     from poasta_b200.sharding import step_family_range
-    batches = [make_families(step_family_range(k, rank, world, F)[0], F, args) for k in range(args.steps)]
-    warm_batches = [make_families(step_family_range(args.steps + w, rank, world, F)[0], F, args) for w in range(min(args.warmup, 2))]
 
-    def step(batch):
-        t0 = time.perf_counter()
-        graphs, scores, cells = msa_batch(batch, device=local, tiebreak=tiebreak)
-        wall = time.perf_counter() - t0
-        kms, launches, _ = aligner.last_batch_stats()
-        sms = aligner.last_batch_search_ms()
-        crit = aligner.last_batch_device_ms()
-        h2d, d2h = aligner.last_batch_io()
-        nseq = sum(len(s) for s in scores)
-        del graphs
-        return [wall, kms, sms, launches, cells, nseq, h2d, d2h, crit]
+    cfg = args.config
+    tiebreak = TIEBREAK_DP if args.tiebreak == "dp" else TIEBREAK_EXACT
+    F = args.families or CONFIGS[cfg]["units"]
+    n_warm_batches = min(args.warmup, 2)
+
+    if cfg == 5:
+        haps, _ = config5_inputs(args, 0, 0)
+        graph = build_config5_graph(haps, device=local)
+        batches = [config5_inputs(args, F, step_family_range(k, rank, world, F)[0])[1] for k in range(args.steps)]
+        warm_batches = [config5_inputs(args, max(64, F // 8), step_family_range(args.steps + w, rank, world, F)[0])[1] for w in range(n_warm_batches)]
+        view = graph.view()
+        real_nodes = graph.node_count()
+
+        def step(batch):
+            t0 = time.perf_counter()
+            res = align_batch([view], batch, [0] * len(batch), AffinePathAware(), AlignmentType.EndsFree, device=local, tiebreak=TIEBREAK_EXACT)
+            wall = time.perf_counter() - t0
+            kms, launches, _ = aligner.last_batch_stats()
+            sms = aligner.last_batch_search_ms()
+            h2d, d2h = aligner.last_batch_io()
+            cells = sum(real_nodes * len(q) for q in batch)
+            del res
+            return [wall, kms, sms, launches, cells, len(batch), h2d, d2h, sms + kms]
+    else:
+        batches = [make_units(cfg, step_family_range(k, rank, world, F)[0], F, args) for k in range(args.steps)]
+        # warm-up batches: the same number of units (same worker pool and buffer sizes as the timed steps) cut to their first three
+        # records, so a warm-up step costs ~1/10 of a timed one
+        def head(fa, n=3):
+            parts = fa.split(b">")
+            return b">".join(parts[:n + 1])
+        warm_batches = [[head(f) for f in make_units(cfg, step_family_range(args.steps + w, rank, world, F)[0], F, args)]
+                        for w in range(n_warm_batches)] if cfg != 4 else [[head(batches[0][0], 4)]]
+
+        def step(batch):
+            t0 = time.perf_counter()
+            graphs, scores, cells = msa_batch(batch, device=local, tiebreak=tiebreak)
+            wall = time.perf_counter() - t0
+            kms, launches, _ = aligner.last_batch_stats()
+            sms = aligner.last_batch_search_ms()
+            crit = aligner.last_batch_device_ms()
+            h2d, d2h = aligner.last_batch_io()
+            nseq = sum(len(s) for s in scores)
+            del graphs
+            return [wall, kms, sms, launches, cells, nseq, h2d, d2h, crit]
 
     for w in range(args.warmup):
         step(warm_batches[w % len(warm_batches)])
@@ -229,31 +334,27 @@ def main():
 
     if rank == 0:
         peak, which = peaks()
-        # dev_ms = device-side critical path: per step the largest per-lane sum of kernel time (CUDA events on the lane's
-        # stream; the pipeline lanes of a rank run their kernels concurrently), max over ranks. dp_ms / search_ms are the
-        # sums over all lanes and launches, i.e. launch durations added up although launches overlap.
         gcups_dev = cells / (dev_ms / 1e3) / 1e9
         gcups_e2e = cells / wall_max / 1e9
         per_rank_cells = cells / world
-        # roofline of the dominant kernel of the step (by device time)
-        dominant = "replay_kernel (order-exact search)" if search_ms > dp_ms else "dp_fill kernels"
-        dom_ms = max(search_ms, dp_ms)
-        # contract: algorithmic bytes per launch / average launch duration = bytes of the step / summed launch durations
+        exact = tiebreak == TIEBREAK_EXACT or cfg == 5
+        if exact:
+            dominant = "msa_engine_kernel (persistent: index build + order-exact search + graph update)" if cfg != 5 else "replay_kernel (order-exact search)"
+            dom_ms, tr = search_ms, measured_traffic("msa_engine_kernel" if cfg != 5 else "replay_kernel")
+            n_dom = args.steps  # one engine launch per step (plus one per extra pass for suspended families)
+        else:
+            dominant, dom_ms, tr = "dp_fill kernels", dp_ms, measured_traffic("dp_fill_warp_kernel")
+            n_dom = max(1, int(launches / world) // 4)
         achieved = per_rank_cells * ALG_BYTES_PER_CU / (dom_ms / 1e3) / 1e9
-        tr = measured_traffic().get("replay_kernel" if search_ms > dp_ms else "dp_fill_warp_kernel")
-        n_dom_launches = max(1, int(launches / world) // (3 if tiebreak == TIEBREAK_EXACT else 4))
-        traffic = tr["dram_bytes_per_cu"] * per_rank_cells / n_dom_launches if tr else None
-        dp_gbs = per_rank_cells * ALG_BYTES_PER_CU / (dp_ms / 1e3) / 1e9 if dp_ms else None
+        traffic = tr["dram_bytes_per_cu"] * per_rank_cells / n_dom if tr else None
         line = {
             "metric": "GCUPS", "value": gcups_dev, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "s32", "data": "synthetic",
-            "config": workload_config(args, F, world),
+            "dtype": "u16" if exact else "s32", "data": "synthetic",
+            "config": workload_config(cfg, args, F, world),
             "seqs_per_s": nseq / wall_max,
-            "device_ms_per_step": {"dp_fill+traceback": dp_ms / args.steps, "order_exact_search": search_ms / args.steps,
-                                   "critical_path": dev_ms / args.steps,
-                                   "note": "the first two are launch durations summed over the concurrent pipeline lanes; "
-                                           "critical_path = the largest per-lane sum, which `value` is quoted on"},
+            "device_ms_per_step": {"dp_fill+traceback": dp_ms / args.steps, "engine_or_search": search_ms / args.steps,
+                                   "critical_path": dev_ms / args.steps},
             "e2e": {"value": gcups_e2e, "unit": "GCUPS", "h2d_bytes_per_step": h2d / world / args.steps,
                     "d2h_bytes_per_step": d2h / world / args.steps, "seqs_per_s": nseq / wall_max},
             "gpu_launches": int(launches),
@@ -261,46 +362,52 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                          "traffic_note": (f"ncu dram__bytes_read+write = {tr['dram_bytes_per_cu']:.2f} B per cell update ({tr['capture']}), "
                                           "scaled to the average launch of this run") if tr else "no ncu capture",
-                         "note": "algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) per launch / average launch "
-                                 "duration (CUDA events); up to 4 launches (pipeline lanes) share the device at a time, so the "
-                                 "device-level rate is `value`. dp_fill_kernel alone: "
-                                 + (f"{dp_gbs:.1f} GB/s = {dp_gbs / peak:.4f} of peak, "
-                                    f"{per_rank_cells * ALG_INT_OPS_PER_CU / (dp_ms / 1e3) / 1e12:.3f} Tint-op/s at 12 ops/CU" if dp_ms else "n/a")},
+                         "note": "algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) x cells of the launch / launch duration "
+                                 "(CUDA events). In reference-exact mode the kernel is the order-exact search, a latency-bound state machine "
+                                 "(one dependent chain of memory round trips per in-flight alignment), not a streaming kernel: its HBM fraction "
+                                 "is small by construction (DESIGN.md section 4)"},
             "clocks": clocks,
         }
-        # integer issue peak of this device, measured after the timed region (the DP fill is integer-bound)
+        if exact and cfg != 5:
+            q_, v_, p_ = aligner.last_batch_search_counts()
+            line["search_counts_last_step"] = {"num_queued": q_, "num_visited": v_, "num_pruned": p_}
         try:
             add_t, min_t, addmin_t = aligner.measure_int_peak(local)
             int_peak = max(add_t, min_t, addmin_t)
-            dp_tops = per_rank_cells * ALG_INT_OPS_PER_CU / (dp_ms / 1e3) / 1e12 if dp_ms else None
-            line["int_roofline"] = {"kernel": "dp_fill kernels", "bound": "integer issue", "unit": "Tint-op/s",
-                                    "achieved": dp_tops, "peak": int_peak, "frac": dp_tops / int_peak if dp_tops else None,
+            path_tops = gcups_dev / world * ALG_INT_OPS_PER_CU / 1e3
+            line["int_roofline"] = {"kernel": "whole device path", "bound": "integer issue", "unit": "Tint-op/s", "achieved": path_tops,
+                                    "peak": int_peak, "frac": path_tops / int_peak,
                                     "peaks_measured": {"add": add_t, "xor+min": min_t, "fused add+min (DPX)": addmin_t},
-                                    "note": "achieved = 12 algorithmic ops per cell update (6*d_v + 6 at in-degree 1) x cells / DP kernel "
-                                            "time summed over the concurrent pipeline lanes; peak = the fastest of three micro-kernels "
-                                            "(8 independent chains per thread, 8 CTAs of 256 threads per SM)"}
+                                    "note": "achieved = value (per GPU) x 12 algorithmic integer ops per cell update (6*d_v + 6 at in-degree 1); peak = "
+                                            "the fastest of three micro-kernels (8 independent chains per thread, 8 CTAs of 256 threads per SM)"}
         except Exception as exc:  # the probe is informative only
             line["int_roofline"] = {"error": str(exc)}
-        if world == 1 and tiebreak == TIEBREAK_EXACT and not args.no_cpu_baseline:
+        if world == 1 and exact and cfg in (2, 3) and not args.no_cpu_baseline:
             # the same workload through the DP-only mode (optimal scores, co-optimal alignments; not bit-exact at ties)
             torch.cuda.synchronize()
+            sub = batches[0][:max(1, len(batches[0]) // 2)]
             t0 = time.perf_counter()
-            g2, s2, c2 = msa_batch(batches[0], device=local, tiebreak=TIEBREAK_DP)
+            g2, s2, c2 = msa_batch(sub, device=local, tiebreak=TIEBREAK_DP)
             w2 = time.perf_counter() - t0
             k2, _, _ = aligner.last_batch_stats()
             del g2
-            line["dp_only_mode"] = {"e2e_gcups": c2 / w2 / 1e9, "seqs_per_s": sum(len(x) for x in s2) / w2, "ms_per_step": w2 * 1e3,
-                                    "kernel_gcups": c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9,
-                                    "note": "tiebreak=dp on step 0's batch after the timed region; kernel time is the sum over "
-                                            "concurrent pipeline lanes"}
+            line["dp_only_mode"] = {"e2e_gcups": c2 / w2 / 1e9, "seqs_per_s": sum(len(x) for x in s2) / w2, "ms": w2 * 1e3,
+                                    "kernel_gcups": c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9, "units": len(sub),
+                                    "note": "tiebreak=dp (DP fill + traceback kernels produce the alignments; host-side graph update) on half of "
+                                            "step 0's batch after the timed region; kernel time is the sum over concurrent pipeline lanes"}
         if world == 1 and not args.no_cpu_baseline:
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-            cores = os.cpu_count() or 1
-            sample = max(4, min(F, cores))
-            s_, c_, q_ = cpu_reference(batches[0][:sample], cores)
+            if cfg == 5:
+                sample = max(8, min(F, 32 * cores))
+                s_, c_ = cpu_reference_reads(graph, batches[0][:sample], cores)
+                q_ = sample
+                what = f"first {sample} reads of step 0, one read per task"
+            else:
+                sample = max(1, min(F, cores if cfg != 3 else 4 * cores))
+                s_, c_, q_ = cpu_reference_msa(batches[0][:sample], cores)
+                what = f"first {sample} {CONFIGS[cfg]['unit']} of step 0, one per task"
             line["cpu_baseline"] = {"value": c_ / s_ / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} families of step 0, one family per task, {cores} threads, "
-                                              f"{s_:.1f} s wall; equivalent GCUPS (A* visits a fraction of the cells)",
+                                    "sample": f"{what}, {cores} threads, {s_:.1f} s wall; equivalent GCUPS (A* visits a fraction of the cells)",
                                     "seqs_per_s": q_ / s_}
         print(json.dumps(line))
     if world > 1:

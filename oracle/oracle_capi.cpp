@@ -268,6 +268,37 @@ double oracle_msa_many(const char *const *fasta, const size_t *fasta_len, uint32
     return secs;
 }
 
+// Many independent reads against ONE fixed graph over a thread pool (config 5, library semantics): PoastaAligner::align per read,
+// which rebuilds the bubble index (and the path index for -H path) for every call (aligner/config.rs:113-134, 296-308).
+// Returns wall seconds; scores (optional) per read, total cells.
+double oracle_align_many(const poasta_graph_view *view, const char *const *seqs, const uint32_t *lens, uint32_t n, int x, int o, int e, int mode,
+                         int heuristic, int n_threads, uint32_t *scores, uint64_t *cells_out, int *err_out) {
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> err{0};
+    AlignOptions opt;
+    opt.costs = Costs{(uint8_t)x, (uint8_t)o, (uint8_t)e};
+    opt.mode = mode, opt.heuristic = heuristic;
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            AstarResult r = astar_align(*view, (const uint8_t *)seqs[i], lens[i], opt);
+            if (r.status) err = r.status;
+            if (scores) scores[i] = r.score;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < n; ++i) c += (uint64_t)(view->n_nodes - 2) * lens[i];
+    *cells_out = c;
+    *err_out = err;
+    return secs;
+}
+
 // Host cost of graph insertion (add_alignment_with_weights + post_process) and CSR flattening for one family: the MSA is built
 // once with the oracle to obtain the alignments, then the insertions are replayed `reps` times. Microseconds per sequence.
 int host_insert_timing(const char *fasta, size_t fasta_len, int reps, double *us_insert, double *us_flatten) {

@@ -64,6 +64,20 @@ def config5(n_haps=50, root_len=20000, hap_rate=0.01, n_reads=1000, read_len=200
     return hap_fa, b"".join(reads)
 
 
+def config5_reads(n_haps, root_len, hap_rate, first, n_reads, read_len=2000, read_rate=0.05):
+    """Config 5 with an explicit read range: (haplotype FASTA, [read first .. first + n_reads) as byte strings)."""
+    hap_fa = family(0xC500000000, n_haps, root_len, hap_rate, prefix="hap")
+    haps = [s for _, s in parse_fasta(hap_fa)]
+    lib = _load()
+    buf = C.create_string_buffer(2 * read_len + 16)
+    reads = []
+    for r in range(first, first + n_reads):
+        h = haps[(r * 2654435761) % n_haps]
+        n = lib.synth_read(0xC500000001 + r, h, len(h), read_len, read_rate, buf, len(buf))
+        reads.append(buf.raw[:n])
+    return hap_fa, reads
+
+
 def parse_fasta(text):
     recs = []
     for block in text.split(b">")[1:]:

@@ -46,6 +46,8 @@ def oracle():
         o.oracle_msa_many.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32] + [C.c_int] * 6 + [
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         o.oracle_msa_many.restype = C.c_double
+        o.oracle_align_many.argtypes = [GV, C.POINTER(C.c_char_p), u32p, C.c_uint32] + [C.c_int] * 6 + [u32p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        o.oracle_align_many.restype = C.c_double
         o.dpmodel_align.argtypes = [GV, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, u32p, u32p, C.c_uint32, u32p, u32p]
         o.dpmodel_align.restype = C.c_uint32
         o.replay_host_align.argtypes = [GV, C.c_char_p, C.c_uint32] + [C.c_int] * 5 + [u32p, u32p, u32p, C.c_uint32, u32p,
@@ -215,6 +217,21 @@ def oracle_msa(fasta, x=4, o=6, e=2, mode=0, heuristic=1, fmt=0, graph_in=None):
         data = C.string_at(out, n.value)
         oracle().oracle_free(out)
     return rc, data, scores[:nseq], cells.value
+
+
+def oracle_align_many(graph, reads, threads, x=4, o=6, e=2, mode=0, heuristic=1, want_scores=False):
+    """Independent reads against one fixed graph with the oracle over `threads` threads: (wall seconds, cells[, scores])."""
+    n = len(reads)
+    ptr = (C.c_char_p * n)(*reads)
+    lens = (C.c_uint32 * n)(*[len(r) for r in reads])
+    scores = np.zeros(max(n, 1), np.uint32)
+    cells, err = C.c_uint64(), C.c_int()
+    view = graph.view() if hasattr(graph, "view") else graph
+    secs = oracle().oracle_align_many(C.byref(view), ptr, lens, n, x, o, e, mode, heuristic, threads, scores.ctypes.data_as(u32p),
+                                      C.byref(cells), C.byref(err))
+    if err.value:
+        raise RuntimeError(f"oracle panic {err.value}")
+    return (secs, cells.value, scores[:n]) if want_scores else (secs, cells.value)
 
 
 def graph_from_seqs(seqs, aligner):
