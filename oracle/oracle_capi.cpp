@@ -386,7 +386,7 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), qwin(rp::QWIN * 3, 0), rb((size_t)view->n_nodes * 2, 0),
         dfa((size_t)(view->n_nodes + 2) * 6, 0);
     // generous arena for the host build: every state can be queued once per successful relaxation
-    const uint32_t max_items = 3 * view->n_nodes * (qlen + 2) + 65536;
+    const uint32_t max_items = (3 * view->n_nodes * (qlen + 2) + 65536) & ~7u;
     const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
     // records {M, D, I, epoch}: zero-filled = "written by no alignment"; this alignment runs as epoch 1 (RP_HOST_EPOCH overrides
     // it and pre-fills the table with records of OTHER epochs, to check that stale records read as unvisited)

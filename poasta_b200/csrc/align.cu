@@ -764,6 +764,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
     // (the inadmissible path heuristic on divergent input re-queues states: high-water 0.99 x cells seen in tools/fuzz_core_vs_oracle.py)
     uint64_t max_items = full_arenas ? 262144 + 2 * cells_per_aln : 32768 + cells_per_aln / 32;
+    max_items = (max_items + 7) & ~(uint64_t)7;  // whole chunks (replay_core.hpp CHUNK)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs

@@ -52,6 +52,11 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 struct WarpSync {
@@ -84,8 +89,10 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
         if (lane == 0) h = atomicAdd(&E.counters[0], 1u);
         h = __shfl_sync(0xFFFFFFFFu, h, 0);
         if (h >= E.n_tickets) break;
-        uint32_t t;
-        while ((t = ld_acquire_u32(&E.tickets[h])) == 0) __nanosleep(500);
+        // spin on a relaxed load; ONE acquire once the slot is filled: an acquire at gpu scope invalidates the SM's whole L1
+        // (CCTL.IVALL), which a polling loop would do to the 31 other workers of the SM every few hundred nanoseconds
+        while (ld_relaxed_u32(&E.tickets[h]) == 0) __nanosleep(1000);
+        const uint32_t t = ld_acquire_u32(&E.tickets[h]);
         if (t == TICKET_NULL) continue;
         const uint32_t f = t - 1;
         dg::Family *F = E.fams + f;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
                     outcome = ENG_SUSPEND;
                 } else {
                     const uint32_t epoch = worker_begin_alignment<CellT>(slab, E.cell_bytes, E.off_qhead, E.off_rb, V, s_qwin[wib], lane);
-                    if (lane == 0) {
+                    {
                         replay::Graph rg;
                         rg.V = V, rg.start = dg::Store::START, rg.end = dg::Store::END;
                         rg.nodes = w.nodes, rg.succ = w.succ, rg.pred = w.pred, rg.bub = w.bub;
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
                         s.max_items = E.max_items;
                         uint32_t *pr = reinterpret_cast<uint32_t *>(slab + E.off_pairs), *pq = pr + E.pair_cap;
                         replay::Search<CellT, HEUR> search(rg, q, Q, E.prm, s);
+                        if (lane == 0) {
                         const long long t_search = clock64();
                         const replay::Result r = search.run(pr, pq, E.pair_cap);
                         out[6] = (uint32_t)((clock64() - t_search) >> 10);
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
                                     outcome = ENG_FAILED, fam_status = rc == dg::DG_CAPACITY ? POASTA_ERR_UNSUPPORTED : POASTA_ERR_INVALID_ALIGNMENT;
                             }
                             out[1] = (uint32_t)fam_status;
+                        }
                         }
                     }
                     outcome = __shfl_sync(0xFFFFFFFFu, outcome, 0);

@@ -33,7 +33,7 @@ struct WorkerLayout {
         const uint64_t cells = (uint64_t)Vw * d.W;
         cell_bytes = up(cells * (cell16 ? 8 : 16));
         f_cap = d.f_max;
-        max_items = (uint32_t)std::min<uint64_t>(0xFFFFFFF0u, full_items ? 262144 + 2 * cells : 32768 + cells / 32);
+        max_items = (uint32_t)std::min<uint64_t>(0xFFFFFFF0u, full_items ? 262144 + 2 * cells : 32768 + cells / 32) & ~7u;  // whole chunks
         pair_cap = Vw + Qmax + 2;
         icap = dg::IndexCaps{Vw, 4 * Vw + 64, 8 * Vw + 64};
         off_qhead = SLAB_CELLS + cell_bytes;

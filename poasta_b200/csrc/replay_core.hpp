@@ -117,8 +117,13 @@ struct Graph {  // node-id space, adjacency in the reference's order
     const uint32_t *path_off, *path_rem;  // sampled-path remainders for -H path (path_off has V + 1 entries)
 };
 
+// Queue items live in CHUNKS of 8 (one 128-byte line): a bucket stack is a chain of chunks, its head word = top slot + 1.
+// `aux` of a chunk's slot 0 = the head word the stack had before the chunk was opened (0 = none). The top items of the
+// stack being popped sit in ONE cache line (two thirds of all pops take the item directly below the previous one), and a
+// chunk is recycled as a whole instead of slot by slot.
+constexpr uint32_t CHUNK = 8;
 struct alignas(16) Item {
-    uint32_t score, node, offset, next;
+    uint32_t score, node, offset, aux;
 };
 
 struct Scratch {  // one slab per in-flight alignment
@@ -126,8 +131,8 @@ struct Scratch {  // one slab per in-flight alignment
     uint32_t epoch;        // epoch of this alignment (1 .. CellT max); records stamped otherwise read as unvisited
     uint32_t *qhead;       // f_max * 3 stack heads (0 = empty, else item index + 1) - authoritative outside the window
     uint32_t *qwin;        // QWIN * 3 heads of priorities [win_base, win_base + QWIN): shared memory on the device
-    Item *items;           // max_items
-    uint32_t *free_slots;  // max_items: stack of recycled item slots (its top stays cache-hot, unlike a list threaded through items)
+    Item *items;           // max_items (multiple of CHUNK), chunk c = slots [8 c, 8 c + 8)
+    uint32_t *free_slots;  // max_items / CHUNK: stack of recycled chunks (its top stays cache-hot, unlike a list threaded through items)
     uint32_t *rb;          // per node [lo, hi + 1] of the reached offsets (hi + 1 == 0: none)
     uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
     uint32_t W, max_items, f_max;
@@ -281,7 +286,7 @@ struct Search {
     const uint32_t Q;
     const Params &p;
     Scratch &s;
-    uint32_t n_items = 0, n_free = 0;  // bump pointer into the item arena; height of the recycled-slot stack
+    uint32_t n_items = 0, n_free = 0;  // bump pointer into the item arena (slots, multiple of CHUNK); height of the recycled-chunk stack
     uint32_t f_cur = 0, f_hi = 0, win_base = 0;
     uint32_t f_top = 0;  // highest priority queued so far: the next alignment of this worker clears qhead[0 .. f_top]
     bool q_empty = true;
@@ -413,19 +418,26 @@ struct Search {
             err = RP_PRIORITY_RANGE;
             return;
         }
-        uint32_t slot;
-        if (n_free) {
-            slot = s.free_slots[--n_free];
-        } else {
-            if (n_items >= s.max_items) {
-                err = RP_OUT_OF_ITEMS;
-                return;
-            }
-            slot = n_items++;
-        }
         if (f > f_top) f_top = f;
         uint32_t *head = head_ptr(f) + st;
-        s.items[slot] = Item{score, node, off, *head};
+        const uint32_t hv = *head;
+        uint32_t slot, aux = 0;
+        if (hv == 0 || (hv & (CHUNK - 1)) == 0) {  // empty stack, or its top chunk is full: open a chunk
+            if (n_free) {
+                slot = s.free_slots[--n_free] * CHUNK;
+            } else {
+                if (n_items + CHUNK > s.max_items) {
+                    err = RP_OUT_OF_ITEMS;
+                    return;
+                }
+                slot = n_items;
+                n_items += CHUNK;
+            }
+            aux = hv;
+        } else {
+            slot = hv;  // the slot above the current top (top = hv - 1)
+        }
+        s.items[slot] = Item{score, node, off, aux};
         *head = slot + 1;
         if (q_empty) {
             f_cur = f_hi = f;
@@ -446,12 +458,18 @@ struct Search {
                 if (head[k]) {
                     const uint32_t slot = head[k] - 1;
                     out = s.items[slot];
+                    uint32_t below;
+                    if ((slot & (CHUNK - 1)) == 0) {  // chunk exhausted: back to the chunk below, recycle this one
+                        below = out.aux;
+                        s.free_slots[n_free++] = slot / CHUNK;
+                    } else {
+                        below = slot;
+                    }
                     RP_STAT(if (slot + 1 == stat_below) RP_CNT(C_NEXT_SAME_STACK);
                             else if (stat_pushes != stat_pushes_at_pop) RP_CNT(C_NEXT_JUST_PUSHED);  // approximation: something was queued since
                             else RP_CNT(C_NEXT_OTHER);
-                            stat_below = out.next; stat_pushes_at_pop = stat_pushes;)
-                    head[k] = out.next;
-                    s.free_slots[n_free++] = slot;
+                            stat_below = below; stat_pushes_at_pop = stat_pushes;)
+                    head[k] = below;
                     st = k;
                     return true;
                 }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
         const RGraphDesc gd = B.graphs[ad.graph];
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
         const uint32_t epoch = worker_begin_alignment<CellT>(slab, B.off_qhead - SLAB_CELLS, B.off_qhead, B.off_rb, gd.V, s_qwin[wib], lane);
-        if (lane == 0) {
+        {
             replay::Graph g;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
             g.nodes = B.nodes + gd.node_base;
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             const long long t_begin = clock64();
 #endif
             replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
+            if (lane == 0) {
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             worker_end_alignment(slab, epoch, search.f_top);
             B.scores[a] = r.score;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
                            100.0 * search.prof_push / total, r.num_visited, r.num_queued, r.num_pruned, total / (r.num_visited ? r.num_visited : 1));
             }
 #endif
+            }
         }
         __syncwarp();
     }

@@ -219,6 +219,20 @@ def oracle_msa(fasta, x=4, o=6, e=2, mode=0, heuristic=1, fmt=0, graph_in=None):
     return rc, data, scores[:nseq], cells.value
 
 
+def oracle_msa_stats(fasta, x=4, o=6, e=2, mode=0, heuristic=1):
+    """(num_queued, num_visited, num_pruned) summed over every alignment of the oracle-driven build of one family."""
+    if isinstance(fasta, str):
+        fasta = fasta.encode()
+    nseq = max(1, fasta.count(b">"))
+    scores = np.zeros(nseq, np.uint32)
+    cells = C.c_uint64()
+    stats = (C.c_uint64 * 3)()
+    rc = oracle().oracle_msa(fasta, len(fasta), None, 0, x, o, e, mode, heuristic, 0, None, None, scores.ctypes.data_as(u32p), nseq,
+                             C.byref(cells), stats)
+    assert rc == 0
+    return tuple(stats)
+
+
 def oracle_align_many(graph, reads, threads, x=4, o=6, e=2, mode=0, heuristic=1, want_scores=False):
     """Independent reads against one fixed graph with the oracle over `threads` threads: (wall seconds, cells[, scores])."""
     n = len(reads)
@@ -226,7 +240,7 @@ def oracle_align_many(graph, reads, threads, x=4, o=6, e=2, mode=0, heuristic=1,
     lens = (C.c_uint32 * n)(*[len(r) for r in reads])
     scores = np.zeros(max(n, 1), np.uint32)
     cells, err = C.c_uint64(), C.c_int()
-    view = graph.view() if hasattr(graph, "view") else graph
+    view = _cview(graph)
     secs = oracle().oracle_align_many(C.byref(view), ptr, lens, n, x, o, e, mode, heuristic, threads, scores.ctypes.data_as(u32p),
                                       C.byref(cells), C.byref(err))
     if err.value:
