@@ -150,13 +150,16 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
         const uint64_t Vmax16 = v16 > (uint64_t)Qmax + 4 ? v16 - Qmax - 4 : 0;
         uint64_t Vw = std::min<uint64_t>(Vworst, std::max<uint64_t>((uint64_t)V0max + 2 * (uint64_t)Qmax + 64, 256));
         bool full_items = false;
+        // test knob: start with workers of this many nodes (families outgrow them and are resumed by later passes)
+        static const uint64_t forced_nodes = getenv("POASTA_WORKER_NODES") ? strtoull(getenv("POASTA_WORKER_NODES"), nullptr, 10) : 0;
+        if (forced_nodes) Vw = std::min<uint64_t>(Vworst, forced_nodes);
         for (int pass = 0; !todo.empty(); ++pass) {
             if (pass > 12) return POASTA_ERR_UNSUPPORTED;
             bool cell16 = Vw <= Vmax16;
             if (const char *e = getenv("POASTA_CELL_BITS")) cell16 = cell16 && atoi(e) == 16;
             // as many nodes per worker as the budget allows while every warp slot (or every family) still gets a worker
             uint64_t want = std::min<uint64_t>(todo.size(), (uint64_t)c.n_sms * 32);
-            if (pass == 0) {
+            if (pass == 0 && !forced_nodes) {
                 uint64_t hi = std::min<uint64_t>(Vworst, cell16 ? Vmax16 : Vworst);
                 while (hi > Vw && WorkerLayout((uint32_t)hi, Qmax, cell16, full_items, prm).total * want > worker_budget)
                     hi = Vw + (hi - Vw) / 2;

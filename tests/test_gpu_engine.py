@@ -36,7 +36,13 @@ def test_ragged_families_and_counters():
             assert g.is_empty()
             continue
         assert rc == 0 and list(sc) == list(osc) and g.to_fasta() == out
-        assert g.to_gfa() == _expect(fa, fmt=1)[0] and g.save() == _expect(fa, fmt=3)[0]
+        assert g.save() == _expect(fa, fmt=3)[0]
+        rc_gfa, gfa, _, _ = H.oracle_msa(fa, fmt=1)
+        if rc_gfa == 0:
+            assert g.to_gfa() == gfa
+        else:  # a walk that starts at `start` (empty record): the reference's GFA writer panics on the missing map key
+            with pytest.raises(OSError):
+                g.to_gfa()
         c += ocells
         st = H.oracle_msa_stats(fa)
         q, v, p = q + st[0], v + st[1], p + st[2]
@@ -64,10 +70,18 @@ def test_all_heuristics_and_ends_free_through_the_engine():
         for fa, g, sc in zip(fastas, graphs, scores):
             out, osc = _expect(fa, heuristic=heur)
             assert g.to_fasta() == out and list(sc) == osc
-    graphs, scores, _ = msa_batch(fastas, aln_type=AlignmentType.EndsFree)
-    for fa, g, sc in zip(fastas, graphs, scores):
-        out, osc = _expect(fa, mode=1)
-        assert g.to_fasta() == out and list(sc) == osc
+    # ends-free stops at the first Match state past offset 0 (gap_affine.rs:202-207), so most builds die in the insert with
+    # InvalidAlignment, in the reference as here (the call reports the first failing family)
+    from poasta_b200 import InvalidAlignment
+    for fa in fastas:
+        rc, out, osc, _ = H.oracle_msa(fa, mode=1)
+        if rc == 0:
+            graphs, scores, _ = msa_batch([fa], aln_type=AlignmentType.EndsFree)
+            assert graphs[0].to_fasta() == out and list(scores[0]) == list(osc)
+        else:
+            assert rc == -4
+            with pytest.raises(InvalidAlignment):
+                msa_batch([fa], aln_type=AlignmentType.EndsFree)
 
 
 _SNIPPET = """
@@ -95,11 +109,11 @@ def _run_with_env(env):
 
 
 def test_families_that_outgrow_their_workers_are_resumed_by_a_second_pass():
-    # a worker budget of 0.02 % of HBM leaves too few nodes per worker for the later rounds: families are suspended with
-    # their graphs intact and finished by further passes with fewer, larger workers
-    out, log = _run_with_env({"POASTA_SLAB_FRACTION": "0.0002"})
+    # workers sized for 330 nodes: the 300 bp families outgrow them after a few rounds, are suspended with their graphs intact and
+    # finished by further passes with larger workers
+    out, log = _run_with_env({"POASTA_WORKER_NODES": "330"})
     assert out["bad"] == 0
-    assert "engine pass 1" in log and " 0 suspended" in log
+    assert "engine pass 1" in log and " 0 suspended" in log and "40 suspended" in log
 
 
 def test_32_bit_score_cells():
