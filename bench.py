@@ -81,7 +81,7 @@ class ClockSampler:
 
 # ---- workloads (seeded per unit, identical for both bench arms) ---------------------------------------
 CONFIGS = {
-    2: dict(name="config2", seqs=20, length=1000, rate=0.05, units=5000, unit="families",
+    2: dict(name="config2", seqs=20, length=1000, rate=0.05, units=6000, unit="families",
             what="synthetic gene families x 20 seqs x 1 kb, 5% subs+indels, global, costs 4/6/2, mingap; progressive MSA (19 rounds)"),
     3: dict(name="config3", seqs=30, length=500, rate=0.10, units=12000, unit="windows",
             what="long-read consensus windows x 30 reads x 500 bp, 10% error, global, costs 4/6/2, mingap; progressive MSA (29 rounds)"),

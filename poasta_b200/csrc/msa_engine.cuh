@@ -78,6 +78,8 @@ __device__ __noinline__ int engine_first(dg::Store &g, const uint8_t *q, uint32_
 
 enum : int { ENG_CONTINUE = 0, ENG_FAILED = 1, ENG_SUSPEND = 2 };
 
+// 16 resident CTAs of 2 warps per SM -> 64 registers, 32 workers per SM. Measured alternatives (profiles/README.md, round 2):
+// 40 registers / 48 workers per SM: 18.2k instead of 13.5k cycles per visited state, 26 % slower at 7,104 families.
 template <typename CellT, int HEUR>
 __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_kernel(EngineDev E) {
     __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];

@@ -167,7 +167,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             }
             WorkerLayout L((uint32_t)Vw, Qmax, cell16, full_items, prm);
             uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want, worker_budget / L.total));
-            const unsigned wpc = workers > (uint64_t)c.n_sms * 16 ? 2 : 1;
+            const unsigned wpc = workers > (uint64_t)c.n_sms * 16 ? 2 : 1;  // at most 32 CTAs are resident per SM
             workers = (workers + wpc - 1) / wpc * wpc;
             if (!eb.workers.reserve(workers * L.total)) {
                 workers = wpc;
