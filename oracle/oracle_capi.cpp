@@ -1,8 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see astar_oracle.hpp header).  C entry points for ctypes.
-// The progressive-MSA driver below restates bin/poasta.rs:163-236 (perform_alignment) on top of
-// the host graph model in poasta_b200/csrc/poa_graph.hpp (graph insertion is host code shared
-// with the product and pinned separately by tests/test_graph_io.py); the ALIGNMENT inside the
-// loop is the oracle's A* restatement, never the CUDA path.
+// Everything here is the oracle's own restatement: the A* path (astar_oracle.hpp), the graph / writers side (poa_oracle.hpp) and
+// the dense model of the DP recurrences (dp_model.hpp). NO product header is included (only the public C header for the
+// poasta_graph_view struct); host builds of product code for CPU-side checks live in tests/hooks/.
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -10,13 +9,9 @@
 #include <cstring>
 #include <thread>
 
-#include "../poasta_b200/csrc/flatten.hpp"
-#include "../poasta_b200/csrc/poa_io.hpp"
 #include "astar_oracle.hpp"
 #include "dp_model.hpp"
-#include "../poasta_b200/csrc/replay_core.hpp"
-#include "../poasta_b200/csrc/search_index.hpp"
-#include "../poasta_b200/csrc/device_batch.hpp"
+#include "poa_oracle.hpp"
 
 using namespace oracle;
 
@@ -179,38 +174,36 @@ void oracle_dfa_event(const poasta_graph_view *view, const uint8_t *symbols_over
 int oracle_msa(const char *fasta, size_t fasta_len, const uint8_t *graph_in, size_t graph_in_len, int x, int o, int e, int mode,
                int heuristic, int fmt, char **out, size_t *out_len, uint32_t *scores, uint32_t scores_cap, uint64_t *cells,
                uint64_t *stats3) {
-    using namespace poasta;
-    POAGraph g;
+    poa::POAGraph g;
     if (graph_in && graph_in_len) {
-        if (!graph_from_poasta(graph_in, graph_in_len, g)) return -8;
+        if (!poa::load_graph(graph_in, graph_in_len, g)) return -8;
     }
-    auto recs = parse_fasta(fasta, fasta_len);
+    const auto recs = poa::read_fasta(fasta, fasta_len);
     AlignOptions opt;
     opt.costs = Costs{(uint8_t)x, (uint8_t)o, (uint8_t)e};
     opt.mode = mode;
     opt.heuristic = heuristic;
-    FlatGraph flat;
     uint64_t ncells = 0;
     uint64_t st[3] = {0, 0, 0};
     for (size_t i = 0; i < recs.size(); ++i) {
         const auto &rec = recs[i];
-        const uint8_t *s = (const uint8_t *)rec.seq.data();
+        const std::vector<uint64_t> weights(rec.seq.size(), 1);  // bin/poasta.rs:193
         uint32_t sc = 0;
-        GraphError ge;
+        poa::Err ge;
         if (g.is_empty()) {
-            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), false, nullptr, 0);
+            ge = g.add_alignment_with_weights(rec.name, rec.seq, nullptr, weights);
         } else {
-            flat.build(g);
+            const poa::Flat flat(g);
             ncells += (uint64_t)g.node_count() * rec.seq.size();
-            AstarResult r = astar_align(flat.view(), s, rec.seq.size(), opt);
+            AstarResult r = astar_align(flat.view, (const uint8_t *)rec.seq.data(), rec.seq.size(), opt);
             if (r.status) return -100 - r.status;
             sc = r.score;
             st[0] += r.num_queued, st[1] += r.num_visited, st[2] += r.num_pruned;
-            std::vector<AlignedPair> aln(r.rpos.size());
+            std::vector<poa::Pair> aln(r.rpos.size());
             for (size_t k = 0; k < aln.size(); ++k) aln[k] = {r.rpos[k], r.qpos[k]};
-            ge = g.add_alignment_with_weights(rec.name, s, rec.seq.size(), true, aln.data(), aln.size());
+            ge = g.add_alignment_with_weights(rec.name, rec.seq, &aln, weights);
         }
-        if (ge != GraphError::Ok) return -(int)ge - 2;
+        if (ge != poa::Err::Ok) return -(int)ge - 2;
         if (scores && i < scores_cap) scores[i] = sc;
     }
     if (cells) *cells = ncells;
@@ -218,16 +211,53 @@ int oracle_msa(const char *fasta, size_t fasta_len, const uint8_t *graph_in, siz
     if (out) {
         std::string buf;
         bool ok = true;
-        if (fmt == 0) ok = graph_to_fasta(g, buf);
-        else if (fmt == 1) ok = graph_to_gfa(g, buf, false);
-        else if (fmt == 2) ok = graph_to_gfa(g, buf, true);
-        else graph_to_poasta(g, buf);
+        if (fmt == 0) ok = poa::graph_to_fasta(g, buf);
+        else if (fmt == 1) ok = poa::graph_to_gfa(g, buf, false);
+        else if (fmt == 2) ok = poa::graph_to_gfa(g, buf, true);
+        else poa::save_graph(g, buf);
         if (!ok) return -8;
         *out = (char *)malloc(buf.size() + 1);
         memcpy(*out, buf.data(), buf.size());
         (*out)[buf.size()] = 0;
         *out_len = buf.size();
     }
+    return 0;
+}
+
+// The oracle's graph side alone, for tests that pin the PRODUCT's graph / writers against it: replays a list of insertions
+// (name, sequence, alignment or None) and returns the requested output. pairs: concatenated (rpos, qpos); n_pairs[i] < 0 = None.
+int oracle_graph_build(const char *const *names, const char *const *seqs, const uint32_t *seq_lens, const uint32_t *pairs, const int64_t *n_pairs,
+                       uint32_t n, const uint8_t *graph_in, size_t graph_in_len, const char *msa_in, size_t msa_in_len, int fmt, char **out,
+                       size_t *out_len, int32_t *insert_status) {
+    poa::POAGraph g;
+    if (graph_in && graph_in_len && !poa::load_graph(graph_in, graph_in_len, g)) return -8;
+    if (msa_in && msa_in_len && !poa::graph_from_fasta_msa(msa_in, msa_in_len, g)) return -5;
+    size_t at = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const std::string seq(seqs[i], seq_lens[i]);
+        const std::vector<uint64_t> weights(seq.size(), 1);
+        poa::Err ge;
+        if (n_pairs[i] < 0) {
+            ge = g.add_alignment_with_weights(names[i], seq, nullptr, weights);
+        } else {
+            std::vector<poa::Pair> aln((size_t)n_pairs[i]);
+            for (auto &p : aln) p = {pairs[2 * at], pairs[2 * at + 1]}, ++at;
+            ge = g.add_alignment_with_weights(names[i], seq, &aln, weights);
+        }
+        if (insert_status) insert_status[i] = (int32_t)ge;
+        if (ge != poa::Err::Ok) return -(int)ge - 2;
+    }
+    std::string buf;
+    bool ok = true;
+    if (fmt == 0) ok = poa::graph_to_fasta(g, buf);
+    else if (fmt == 1) ok = poa::graph_to_gfa(g, buf, false);
+    else if (fmt == 2) ok = poa::graph_to_gfa(g, buf, true);
+    else poa::save_graph(g, buf);
+    if (!ok) return -8;
+    *out = (char *)malloc(buf.size() + 1);
+    memcpy(*out, buf.data(), buf.size());
+    (*out)[buf.size()] = 0;
+    *out_len = buf.size();
     return 0;
 }
 
@@ -299,50 +329,6 @@ double oracle_align_many(const poasta_graph_view *view, const char *const *seqs,
     return secs;
 }
 
-// Host cost of graph insertion (add_alignment_with_weights + post_process) and CSR flattening for one family: the MSA is built
-// once with the oracle to obtain the alignments, then the insertions are replayed `reps` times. Microseconds per sequence.
-int host_insert_timing(const char *fasta, size_t fasta_len, int reps, double *us_insert, double *us_flatten) {
-    using namespace poasta;
-    auto recs = parse_fasta(fasta, fasta_len);
-    AlignOptions opt;
-    opt.costs = Costs{4, 6, 2};
-    opt.mode = 0, opt.heuristic = 1;
-    std::vector<std::vector<AlignedPair>> alns(recs.size());
-    {
-        POAGraph g;
-        FlatGraph flat;
-        for (size_t i = 0; i < recs.size(); ++i) {
-            const uint8_t *s = (const uint8_t *)recs[i].seq.data();
-            if (!g.is_empty()) {
-                flat.build(g);
-                AstarResult r = astar_align(flat.view(), s, recs[i].seq.size(), opt);
-                if (r.status) return -1;
-                alns[i].resize(r.rpos.size());
-                for (size_t k = 0; k < alns[i].size(); ++k) alns[i][k] = {r.rpos[k], r.qpos[k]};
-            }
-            g.add_alignment_with_weights(recs[i].name, s, recs[i].seq.size(), i != 0, alns[i].data(), alns[i].size());
-        }
-    }
-    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_ins = 0, t_flat = 0;
-    for (int rep = 0; rep < reps; ++rep) {
-        POAGraph g;
-        FlatGraph flat;
-        for (size_t i = 0; i < recs.size(); ++i) {
-            const uint8_t *s = (const uint8_t *)recs[i].seq.data();
-            const double t0 = now();
-            g.add_alignment_with_weights(recs[i].name, s, recs[i].seq.size(), i != 0, alns[i].data(), alns[i].size());
-            const double t1 = now();
-            flat.build(g);
-            const double t2 = now();
-            t_ins += t1 - t0, t_flat += t2 - t1;
-        }
-    }
-    *us_insert = t_ins / (reps * (double)recs.size());
-    *us_flatten = t_flat / (reps * (double)recs.size());
-    return 0;
-}
-
 // Dense DP model (dp_model.hpp): global mode. Returns score (0x3FFFFFFF when unreachable).
 uint32_t dpmodel_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, uint32_t *rpos,
                        uint32_t *qpos, uint32_t cap, uint32_t *n_pairs, uint32_t *tables_out) {
@@ -361,148 +347,6 @@ uint32_t dpmodel_align(const poasta_graph_view *view, const uint8_t *seq, uint32
         memcpy(tables_out + 2 * n, t.I.data(), n * 4);
     }
     return score;
-}
-
-// Host build of the product's order-exact search core (poasta_b200/csrc/replay_core.hpp), for CPU-side tests of the
-// logic that runs on the device. TEST HOOK ONLY: the product never executes this path (it has no CPU fallback).
-int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, int mode,
-                      int heuristic, uint32_t *score, uint32_t *rpos, uint32_t *qpos, uint32_t cap, uint32_t *n_pairs,
-                      uint64_t *stats, int cell16) {
-    namespace rp = poasta::replay;
-    using rp::Item;
-    using rp::Params;
-    using rp::Result;
-    using rp::Scratch;
-    using rp::ScratchDims;
-    poasta::SearchIndex si;
-    si.build(*view, heuristic == 2);
-    std::vector<rp::NodeRec> recs;
-    si.node_records(*view, recs);
-    std::vector<uint32_t> path_off_zero;
-    if (si.path_off.empty()) path_off_zero.assign(view->n_nodes + 1, 0);
-    rp::Graph g{view->n_nodes, view->start_node, view->end_node, recs.data(), view->succ, view->pred, reinterpret_cast<const rp::BubQ *>(si.bub.data()),
-                si.path_off.empty() ? path_off_zero.data() : si.path_off.data(), si.path_rem.empty() ? nullptr : si.path_rem.data()};
-    ScratchDims d(view->n_nodes, qlen, x, o, e);
-    std::vector<uint32_t> qhead((size_t)d.f_max * 3, 0), qwin(rp::QWIN * 3, 0), rb((size_t)view->n_nodes * 2, 0),
-        dfa((size_t)(view->n_nodes + 2) * 6, 0);
-    // generous arena for the host build: every state can be queued once per successful relaxation
-    const uint32_t max_items = (3 * view->n_nodes * (qlen + 2) + 65536) & ~7u;
-    const uint64_t plane_elems = (uint64_t)view->n_nodes * d.W;
-    // records {M, D, I, epoch}: zero-filled = "written by no alignment"; this alignment runs as epoch 1 (RP_HOST_EPOCH overrides
-    // it and pre-fills the table with records of OTHER epochs, to check that stale records read as unvisited)
-    std::vector<uint8_t> planes((size_t)4 * plane_elems * (cell16 ? 2 : 4), 0);
-    uint32_t epoch = 1;
-    if (const char *ep = getenv("RP_HOST_EPOCH")) {
-        epoch = (uint32_t)atoi(ep);
-        uint32_t x = 12345;
-        for (size_t i = 0; i < planes.size(); i += (cell16 ? 8 : 16)) {  // garbage scores stamped with epochs != epoch
-            for (int k = 0; k < (cell16 ? 8 : 16); ++k) planes[i + k] = (uint8_t)((x = x * 1664525u + 1013904223u) >> 24);
-            uint32_t other = (x >> 8) % 0xFFFEu + 1;
-            if (other == epoch) other = epoch == 1 ? 2 : epoch - 1;
-            if (cell16) ((uint16_t *)(planes.data() + i))[3] = (uint16_t)other;
-            else ((uint32_t *)(planes.data() + i))[3] = other;
-        }
-    }
-    std::vector<Item> items(max_items);
-    std::vector<uint32_t> free_slots(max_items);
-    Scratch s{planes.data(), epoch, qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), d.W, max_items, d.f_max};
-    Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
-    const uint32_t ocap = view->n_nodes + qlen + 2;
-    std::vector<uint32_t> out_r(ocap), out_q(ocap);
-    Result r;
-    uint32_t used_blocks = 0, used_items = 0;
-    auto go = [&](auto cell, auto heur) {
-        rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
-        r = search.run(out_r.data(), out_q.data(), ocap);
-        used_items = search.n_items;
-    };
-    auto go_cell = [&](auto cell) {
-        if (heuristic == 0) go(cell, std::integral_constant<int, 0>{});
-        else if (heuristic == 1) go(cell, std::integral_constant<int, 1>{});
-        else go(cell, std::integral_constant<int, 2>{});
-    };
-    if (cell16) go_cell(uint16_t{});
-    else go_cell(uint32_t{});
-    *score = r.score;
-    *n_pairs = r.n_pairs;
-    for (uint32_t i = 0; i < r.n_pairs && i < cap; ++i) {
-        rpos[i] = out_r[ocap - r.n_pairs + i];
-        qpos[i] = out_q[ocap - r.n_pairs + i];
-    }
-    if (stats) stats[0] = r.num_queued, stats[1] = r.num_visited, stats[2] = r.num_pruned, stats[3] = used_blocks, stats[4] = used_items;
-    return r.status;
-}
-
-// The product's host-side packing of one graph for the DP kernels (device_batch.hpp) and its node records for the search
-// kernel (search_index.hpp), dumped so CPU tests can pin the layouts the device code reads. TEST HOOK ONLY.
-//   meta[4] = V, max_in_degree, n_stored, n_ord_rows; rows = 4 words per row (RowRec); recs = 8 words per node (NodeRec)
-int packed_graph_dump(const poasta_graph_view *view, uint32_t *meta, uint32_t *rows, uint32_t *node_info, uint32_t *node_id,
-                      uint32_t *ord_slot, uint32_t *pred_off, uint32_t *pred_rank, uint32_t *pred_slot, uint8_t *node_sym, uint32_t *recs) {
-    poasta::PackedGraph pg;
-    std::vector<uint32_t> scratch;
-    pg.build(*view, scratch);
-    meta[0] = pg.V, meta[1] = pg.max_in_degree, meta[2] = pg.n_stored, meta[3] = pg.n_ord_rows;
-    static_assert(sizeof(poasta::RowRec) == 16 && sizeof(poasta::replay::NodeRec) == 32, "device record sizes");
-    memcpy(rows, pg.rows.data(), pg.rows.size() * sizeof(poasta::RowRec));
-    memcpy(node_info, pg.node_info.data(), pg.node_info.size() * 4);
-    memcpy(node_id, pg.node_id.data(), pg.node_id.size() * 4);
-    memcpy(ord_slot, pg.ord_slot.data(), pg.ord_slot.size() * 4);
-    memcpy(pred_off, pg.pred_off.data(), pg.pred_off.size() * 4);
-    memcpy(pred_rank, pg.pred_rank.data(), pg.pred_rank.size() * 4);
-    memcpy(pred_slot, pg.pred_slot.data(), pg.pred_slot.size() * 4);
-    memcpy(node_sym, pg.node_sym.data(), pg.node_sym.size());
-    poasta::SearchIndex si;
-    si.build(*view, false);
-    std::vector<poasta::replay::NodeRec> nr;
-    si.node_records(*view, nr);
-    memcpy(recs, nr.data(), nr.size() * sizeof(poasta::replay::NodeRec));
-    return 0;
-}
-
-// The PRODUCT's search index (poasta_b200/csrc/search_index.hpp) in the same shape as oracle_bubble_index, so tests can
-// compare the two restatements entry by entry. TEST HOOK ONLY.
-void product_bubble_index(const poasta_graph_view *view, uint32_t max_per_node, uint32_t *counts, uint32_t *out_maps, uint32_t *dist,
-                          uint8_t *is_exit) {
-    poasta::SearchIndex si;
-    si.build(*view, false);
-    for (uint32_t n = 0; n < view->n_nodes; ++n) {
-        counts[n] = si.bub_off[n + 1] - si.bub_off[n];
-        for (uint32_t k = 0; k < counts[n] && k < max_per_node; ++k) {
-            const uint32_t *q = si.bub.data() + 4 * (size_t)(si.bub_off[n] + k);
-            uint32_t *o = out_maps + 3 * ((size_t)n * max_per_node + k);
-            o[0] = q[0], o[1] = q[1], o[2] = q[2];
-            // the fourth word is derived: min_dist_to_end of the exit used by the prune test (reached.rs:57-58)
-            if (q[3] != (si.dist_min[q[0]] ? si.dist_min[q[0]] - 1 : 0)) counts[n] = 0xFFFFFFFFu;
-        }
-        dist[2 * n] = si.dist_min[n], dist[2 * n + 1] = si.dist_max[n];
-        is_exit[n] = si.is_exit[n];
-    }
-}
-
-// Host cost of the per-round preparation the product does for every graph (search index, DP packing, node records):
-// milliseconds per call, averaged over `reps`. TEST / MEASUREMENT HOOK ONLY.
-int host_prep_timing(const poasta_graph_view *view, int reps, double *ms_index, double *ms_pack, double *ms_recs) {
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    poasta::SearchIndex si;
-    poasta::PackedGraph pg;
-    std::vector<uint32_t> scratch;
-    std::vector<poasta::replay::NodeRec> nr;
-    double t0 = now();
-    for (int i = 0; i < reps; ++i) si.build(*view, false);
-    double t1 = now();
-    for (int i = 0; i < reps; ++i) pg.build(*view, scratch);
-    double t2 = now();
-    for (int i = 0; i < reps; ++i) nr.clear(), si.node_records(*view, nr);
-    double t3 = now();
-    *ms_index = (t1 - t0) / reps, *ms_pack = (t2 - t1) / reps, *ms_recs = (t3 - t2) / reps;
-    return 0;
-}
-
-// event counters of the host build of the search core (tools/search_stats.py); reading resets them
-int replay_host_counters(uint64_t *out, int cap) {
-    namespace rp = poasta::replay;
-    for (int i = 0; i < rp::C_N && i < cap; ++i) out[i] = rp::rp_counters[i], rp::rp_counters[i] = 0;
-    return rp::C_N;
 }
 
 void oracle_free(void *p) { free(p); }

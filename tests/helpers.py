@@ -13,19 +13,34 @@ from poasta_b200.graph import NONE, AlignedPair, POAGraph
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_PATH = os.path.join(ROOT, "oracle", "liboracle.so")
+HOOKS_PATH = os.path.join(ROOT, "tests", "hooks", "libproduct_hooks.so")
 _oracle = None
+_hooks = None
 
 MATCH, DELETION, INSERTION = 0, 1, 2
 u32p = C.POINTER(C.c_uint32)
 u8p = C.POINTER(C.c_uint8)
 
 
+class _Both:
+    """Symbols of the oracle library first, of the product-hook library (host builds of product headers) second."""
+
+    def __init__(self, a, b):
+        self._a, self._b = a, b
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._a, name)
+        except AttributeError:
+            return getattr(self._b, name)
+
+
 def oracle():
     global _oracle
     if _oracle is None:
-        if not os.path.exists(ORACLE_PATH):
-            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-        o = C.CDLL(ORACLE_PATH)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hooks")], check=True, capture_output=True)
+        o = _Both(C.CDLL(ORACLE_PATH), C.CDLL(HOOKS_PATH))
         GV = C.POINTER(plib.GraphView)
         o.oracle_align.argtypes = [GV, C.c_char_p, C.c_uint32] + [C.c_int] * 6 + [u32p, u32p, u32p, C.c_uint32, u32p,
                                                                                  C.POINTER(C.c_uint64)]

@@ -44,3 +44,11 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"oracle/|liboracle|astar_oracle|dp_model", text):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_oracle_does_not_include_the_product():
+    """The oracle library is built from oracle/ alone (plus the public C header for one struct): no product header or source."""
+    for f in os.listdir(os.path.join(ROOT, "oracle")):
+        if f.endswith((".cpp", ".hpp", ".h")) or f == "Makefile":
+            text = open(os.path.join(ROOT, "oracle", f), errors="ignore").read()
+            assert not re.search(r'#include\s+"[^"]*poasta_b200/|csrc/', text), f

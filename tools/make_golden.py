@@ -1,7 +1,10 @@
 """Writes tests/golden/*.expected.{fa,gfa,scores}: `poasta align` output of the ORACLE (the CPU restatement of the reference)
-for the reference's own test inputs, default options (-n 4 -g 6 -e 2 -m global -H mingap). They freeze the restated
-behaviour so that any later change of the oracle or the product shows up as a byte difference; they were NOT produced by
-the real reference binary (no Rust toolchain in this image, DESIGN.md section 5: whole-MSA parity is unpinned).
+for the reference's own test inputs, default options (-n 4 -g 6 -e 2 -m global -H mingap). Since round 2 the oracle is an
+independent restatement (aligner, graph and writers share no code with the product), so these files are "oracle-frozen", not
+"self-frozen": the product must reproduce them on the CPU (graph / writers) and on the GPU (whole MSA). They were NOT produced
+by the real reference binary (no Rust toolchain in this image, DESIGN.md section 5: whole-MSA parity stays unpinned).
+Note: the reference's own tests/small_test.truth.fa differs from small_test.expected.fa by design: it has 6 leading gaps where
+the current io/fasta.rs writer emits `col - 1` = 5 (saturating_sub); no reference test opens that file.
 usage: python tools/make_golden.py"""
 import os
 import sys
