@@ -117,10 +117,12 @@ uint32_t poasta_graph_node_count_with_start_and_end(const poasta_graph *g);
 uint32_t poasta_graph_edge_count(const poasta_graph *g);               /* poa.rs:409 */
 uint32_t poasta_graph_num_sequences(const poasta_graph *g);
 /* POAGraph::add_alignment_with_weights (poa.rs:171-321); rpos == NULL means alignment None;
- * weights == NULL means all ones (bin/poasta.rs:193). */
+ * weights == NULL means all ones (bin/poasta.rs:193), else weights_len must equal len
+ * (POASTA_ERR_WEIGHTS_UNEQUAL, poa.rs:178-180). Pairs that name a node or a query position out of
+ * range return POASTA_ERR_INVALID_ALIGNMENT (the reference panics on the index). */
 int poasta_graph_add_alignment(poasta_graph *g, const char *name, const uint8_t *seq, uint32_t len,
                                const uint32_t *rpos, const uint32_t *qpos, uint32_t n_pairs,
-                               const uint64_t *weights);
+                               const uint64_t *weights, uint32_t weights_len);
 /* Borrowed CSR view, valid until the next mutation of `g`. */
 int poasta_graph_get_view(poasta_graph *g, poasta_graph_view *view);
 /* aligned_nodes of one node (poa.rs:374); returns count, writes up to cap ids. */

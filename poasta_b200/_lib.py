@@ -67,7 +67,7 @@ def load():
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = C.c_uint32
     lib.poasta_graph_add_alignment.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint32, u32p, u32p,
-                                               C.c_uint32, C.POINTER(C.c_uint64)]
+                                               C.c_uint32, C.POINTER(C.c_uint64), C.c_uint32]
     lib.poasta_graph_get_view.argtypes = [vp, C.POINTER(GraphView)]
     lib.poasta_graph_aligned_nodes.argtypes = [vp, C.c_uint32, u32p, C.c_uint32]
     lib.poasta_graph_aligned_nodes.restype = C.c_uint32

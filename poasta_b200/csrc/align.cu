@@ -668,6 +668,8 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
 
 // memory budget for one chunk's trace store
 static uint64_t trace_budget_bytes() {
+    static const uint64_t forced_mb = getenv("POASTA_DP_BUDGET_MB") ? strtoull(getenv("POASTA_DP_BUDGET_MB"), nullptr, 10) : 0;  // test knob
+    if (forced_mb) return forced_mb << 20;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (uint64_t)8 << 30;
     return std::max<uint64_t>((uint64_t)1 << 30, std::min<uint64_t>((uint64_t)48 << 30, total_b / 3)) / tl_lane_count;
@@ -702,6 +704,9 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
         pb.clear();
         idx.clear();
         uint32_t last_key = 0xFFFFFFFFu, last_gid = 0;
+        uint64_t chunk_bytes = 0, merge_rows = 0;
+        uint32_t budget_key = 0;
+        bool have_budget_key = false;
         while (i < n) {
             const Problem &p = probs[i];
             const uint64_t V = p.graph->n_nodes;
@@ -710,8 +715,17 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
                 ++i;
                 continue;
             }
-            const uint64_t add = V * ((p.qlen + 4) & ~3ull) * 4;
-            if (!pb.alns.empty() && (pb.trace_elems * 2 + add > budget || pb.alns.size() >= (1u << 20))) break;
+            // what run_chunk will allocate for this alignment, whichever kernel it picks: the CTA kernel keeps one trace word per
+            // cell (2 or 4 bytes), the warp kernel 1 KB of bit planes per row plus a 4 KB ordinal block per row with >= 2
+            // predecessors, independent of the query length (so short queries are NOT cheap there)
+            if (p.graph_key != budget_key || !have_budget_key) {
+                merge_rows = 0;
+                for (uint32_t v = 0; v < p.graph->n_nodes; ++v) merge_rows += p.graph->pred_off[v + 1] - p.graph->pred_off[v] >= 2;
+                budget_key = p.graph_key, have_budget_key = true;
+            }
+            const uint64_t add = std::max<uint64_t>(V * ((p.qlen + 4) & ~3ull) * 4, V * 1024 + merge_rows * 4096);
+            if (!pb.alns.empty() && (chunk_bytes + add > budget || pb.alns.size() >= (1u << 20))) break;
+            chunk_bytes += add;
             if (p.graph_key != last_key || pb.graphs.empty()) {
                 last_gid = p.packed ? pb.add_packed(*p.packed) : pb.add_graph(*p.graph, rank_scratch);
                 last_key = p.graph_key;
@@ -984,7 +998,36 @@ static int replay_problems(int device, const std::vector<Problem> &probs, const 
 // Dispatch on poasta_params::tiebreak (include/poasta_b200.h).
 template <class Sink>
 static int align_problems(int device, const std::vector<Problem> &probs, const poasta_params &prm, Sink &&sink) {
-    if (prm.tiebreak == 1) return dp_problems(device, probs, prm, sink);
+    if (prm.tiebreak == 1) {
+        // an EMPTY query against a non-empty graph has no DP table to fill; the reference aligns it (all deletions along the
+        // cheapest path, empty alignment), and so does the search kernel: those problems take that path in DP mode too
+        std::vector<size_t> q0, rest;
+        for (size_t i = 0; i < probs.size(); ++i) (probs[i].qlen == 0 && probs[i].graph->n_nodes > 2 ? q0 : rest).push_back(i);
+        if (q0.empty()) return dp_problems(device, probs, prm, sink);
+        std::vector<Problem> a, b;
+        for (size_t i : q0) a.push_back(probs[i]);
+        for (size_t i : rest) b.push_back(probs[i]);
+        struct Held {
+            uint32_t score;
+            int32_t status;
+            std::vector<uint32_t> r, q;
+        };
+        std::vector<Held> held(probs.size());
+        auto keep = [&](const std::vector<size_t> &map) {
+            return [&held, &map](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
+                Held &h = held[map[i]];
+                h.score = score, h.status = status;
+                h.r.assign(r, r + np), h.q.assign(q, q + np);
+            };
+        };
+        int rc = replay_problems(device, a, prm, keep(q0));
+        if (rc) return rc;
+        tl_search_stats.clear();
+        rc = dp_problems(device, b, prm, keep(rest));
+        if (rc) return rc;
+        for (size_t i = 0; i < probs.size(); ++i) sink(i, held[i].score, held[i].status, held[i].r.data(), held[i].q.data(), (uint32_t)held[i].r.size());
+        return 0;
+    }
     if (prm.mode != 0) return replay_problems(device, probs, prm, sink);  // ends-free exists only as a search-order property
     // reference-exact, global: the DP kernels give the optimal score of every problem, the search gives the alignment;
     // the two scores must agree (device-side self check of both paths)

@@ -18,6 +18,17 @@ static int map_graph_error(GraphError e) {
     return POASTA_ERR_INVALID_ARG;
 }
 
+// No C++ exception may cross the C boundary: allocation failures (e.g. on a crafted graph file) become a status.
+template <class F> static int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return POASTA_ERR_IO;
+    } catch (...) {
+        return POASTA_ERR_INTERNAL;
+    }
+}
+
 static int emit(const std::string &buf, char **out, size_t *len) {
     char *p = (char *)malloc(buf.size() + 1);
     if (!p) return POASTA_ERR_IO;
@@ -38,13 +49,21 @@ uint32_t poasta_graph_edge_count(const poasta_graph *g) { return g->g.edge_count
 uint32_t poasta_graph_num_sequences(const poasta_graph *g) { return (uint32_t)g->g.sequences.size(); }
 
 int poasta_graph_add_alignment(poasta_graph *h, const char *name, const uint8_t *seq, uint32_t len, const uint32_t *rpos,
-                               const uint32_t *qpos, uint32_t n_pairs, const uint64_t *weights) {
+                               const uint32_t *qpos, uint32_t n_pairs, const uint64_t *weights, uint32_t weights_len) {
     if (!h || !name || (len && !seq)) return POASTA_ERR_INVALID_ARG;
-    h->flat_valid = false;
-    if (!rpos || !qpos) return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, false, nullptr, 0, weights));
-    std::vector<AlignedPair> aln(n_pairs);
-    for (uint32_t i = 0; i < n_pairs; ++i) aln[i] = {rpos[i], qpos[i]};
-    return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, true, aln.data(), n_pairs, weights));
+    if (weights && weights_len != len) return POASTA_ERR_WEIGHTS_UNEQUAL;  // poa.rs:178-180
+    return guarded([&]() -> int {
+        h->flat_valid = false;
+        if (!rpos || !qpos) return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, false, nullptr, 0, weights));
+        // the reference indexes graph[rpos] and sequence[qpos] and panics when they are out of range; here that is a status
+        const uint32_t nn = h->g.node_count_with_start_and_end();
+        std::vector<AlignedPair> aln(n_pairs);
+        for (uint32_t i = 0; i < n_pairs; ++i) {
+            if ((rpos[i] != NIL && rpos[i] >= nn) || (qpos[i] != NIL && qpos[i] >= len)) return POASTA_ERR_INVALID_ALIGNMENT;
+            aln[i] = {rpos[i], qpos[i]};
+        }
+        return map_graph_error(h->g.add_alignment_with_weights(name, seq, len, true, aln.data(), n_pairs, weights));
+    });
 }
 
 int poasta_graph_get_view(poasta_graph *h, poasta_graph_view *view) {
@@ -66,52 +85,83 @@ uint32_t poasta_graph_aligned_nodes(const poasta_graph *h, uint32_t node, uint32
 }
 
 int poasta_graph_to_fasta(const poasta_graph *h, char **out, size_t *len) {
-    std::string buf;
-    if (!graph_to_fasta(h->g, buf)) return POASTA_ERR_IO;
-    return emit(buf, out, len);
+    if (!h || !out || !len) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        std::string buf;
+        if (!graph_to_fasta(h->g, buf)) return POASTA_ERR_IO;
+        return emit(buf, out, len);
+    });
 }
 
 int poasta_graph_to_gfa(const poasta_graph *h, int v1, char **out, size_t *len) {
-    std::string buf;
-    if (!graph_to_gfa(h->g, buf, v1 != 0)) return POASTA_ERR_IO;
-    return emit(buf, out, len);
+    if (!h || !out || !len) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        std::string buf;
+        if (!graph_to_gfa(h->g, buf, v1 != 0)) return POASTA_ERR_IO;
+        return emit(buf, out, len);
+    });
 }
 
 int poasta_graph_to_dot(const poasta_graph *h, int dialect, char **out, size_t *len) {
-    std::string buf;
-    if (dialect == 0) graph_to_dot_view(h->g, buf);
-    else graph_to_dot_petgraph(h->g, buf);
-    return emit(buf, out, len);
+    if (!h || !out || !len) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        std::string buf;
+        if (dialect == 0) graph_to_dot_view(h->g, buf);
+        else graph_to_dot_petgraph(h->g, buf);
+        return emit(buf, out, len);
+    });
 }
 
 int poasta_graph_save(const poasta_graph *h, char **out, size_t *len) {
-    std::string buf;
-    graph_to_poasta(h->g, buf);
-    return emit(buf, out, len);
+    if (!h || !out || !len) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        std::string buf;
+        graph_to_poasta(h->g, buf);
+        return emit(buf, out, len);
+    });
 }
 
 int poasta_graph_load(const uint8_t *data, size_t len, poasta_graph **out) {
-    poasta_graph *h = new (std::nothrow) poasta_graph();
-    if (!h) return POASTA_ERR_IO;
-    if (!graph_from_poasta(data, len, h->g)) {
-        delete h;
-        return POASTA_ERR_IO;
-    }
-    *out = h;
-    return POASTA_OK;
+    if (!data || !out) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        poasta_graph *h = new (std::nothrow) poasta_graph();
+        if (!h) return POASTA_ERR_IO;
+        bool ok = false;
+        try {
+            ok = graph_from_poasta(data, len, h->g);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        if (!ok) {
+            delete h;
+            return POASTA_ERR_IO;
+        }
+        *out = h;
+        return POASTA_OK;
+    });
 }
 
 int poasta_graph_from_fasta_msa(const char *fasta, size_t len, poasta_graph **out) {
-    poasta_graph *h = new (std::nothrow) poasta_graph();
-    if (!h) return POASTA_ERR_IO;
-    auto recs = parse_fasta(fasta, len);
-    GraphError e = graph_from_fasta_msa(recs, h->g);
-    if (e != GraphError::Ok) {
-        delete h;
-        return map_graph_error(e);
-    }
-    *out = h;
-    return POASTA_OK;
+    if (!fasta || !out) return POASTA_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        poasta_graph *h = new (std::nothrow) poasta_graph();
+        if (!h) return POASTA_ERR_IO;
+        GraphError e;
+        try {
+            auto recs = parse_fasta(fasta, len);
+            e = graph_from_fasta_msa(recs, h->g);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        if (e != GraphError::Ok) {
+            delete h;
+            return map_graph_error(e);
+        }
+        *out = h;
+        return POASTA_OK;
+    });
 }
 
 void poasta_free_buffer(void *p) { free(p); }

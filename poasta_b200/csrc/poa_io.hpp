@@ -441,33 +441,43 @@ inline void graph_to_poasta(const POAGraph &g, std::string &out) {
     w.u32(g.end_node);
 }
 
+// Reads a .poasta file. The file is UNTRUSTED input (`view`, `stats`, `align -I`): every count is bounded by the bytes that
+// are left before anything is allocated, every node id is checked against the node count, and the topological order is
+// recomputed instead of trusted (the reference's bincode + petgraph deserialisers reject or panic on such files).
 inline bool graph_from_poasta(const uint8_t *data, size_t len, POAGraph &g) {
     BinReader r{data, data + len};
+    auto left = [&]() { return (uint64_t)(r.end - r.p); };
     if (r.u32() != 2) return false;  // only the U32 variant is produced by the CLI (bin/poasta.rs:316)
     g = POAGraph();
     g.nodes.clear();
-    uint64_t nn = r.u64();
-    if (!r.ok || nn > (1ull << 31)) return false;
-    for (uint64_t i = 0; i < nn && r.ok; ++i) {
+    const uint64_t nn = r.u64();
+    if (!r.ok || nn < 2 || nn > (1ull << 31) || nn > left() / 9) return false;  // a node is at least 9 bytes
+    for (uint64_t i = 0; i < nn; ++i) {
         POAGraph::Node nd{r.u8(), {NIL, NIL}, {}};
-        uint64_t na = r.u64();
-        if (!r.ok || na > nn) return false;
-        for (uint64_t k = 0; k < na; ++k) nd.aligned_nodes.push_back(r.u32());
+        const uint64_t na = r.u64();
+        if (!r.ok || na > nn || na > left() / 4) return false;
+        for (uint64_t k = 0; k < na; ++k) {
+            const uint32_t a = r.u32();
+            if (a >= nn) return false;
+            nd.aligned_nodes.push_back(a);
+        }
         g.nodes.push_back(std::move(nd));
     }
     if (r.u64() != 0) return false;  // node holes never occur (nodes are never removed)
     r.u32();
-    uint64_t ne = r.u64();
-    if (!r.ok || ne > (1ull << 32)) return false;
+    const uint64_t ne = r.u64();
+    if (!r.ok || ne > (1ull << 32) - 2 || ne > left()) return false;  // a slot is at least 1 byte
     // Rebuild adjacency exactly as petgraph's deserializer does: edges re-added in slot order
     // (so list heads are the highest slots), vacant slots chained on the free list afterwards.
     g.edges.clear();
     g.free_edge = NIL;
     g.live_edges = 0;
     g.edges.resize(ne);
-    for (uint64_t i = 0; i < ne && r.ok; ++i) {
+    for (uint64_t i = 0; i < ne; ++i) {
         POAGraph::Edge &e = g.edges[i];
-        if (r.u8() == 0) {
+        const uint8_t tag = r.u8();
+        if (!r.ok || tag > 1) return false;
+        if (tag == 0) {
             e.vacant = true;
             e.node[0] = e.node[1] = NIL;
             e.next[0] = g.free_edge;
@@ -480,8 +490,8 @@ inline bool graph_from_poasta(const uint8_t *data, size_t len, POAGraph &g) {
         e.node[0] = r.u32();
         e.node[1] = r.u32();
         e.weight = r.u64();
-        uint64_t ns = r.u64();
-        if (!r.ok || e.node[0] >= nn || e.node[1] >= nn || ns > (1ull << 32)) return false;
+        const uint64_t ns = r.u64();
+        if (!r.ok || e.node[0] >= nn || e.node[1] >= nn || ns > left() / 8) return false;
         for (uint64_t k = 0; k < ns; ++k) e.sequence_ids.push_back(r.u64());
         e.next[0] = g.nodes[e.node[0]].head[0];
         e.next[1] = g.nodes[e.node[1]].head[1];
@@ -489,21 +499,36 @@ inline bool graph_from_poasta(const uint8_t *data, size_t len, POAGraph &g) {
         g.nodes[e.node[1]].head[1] = (uint32_t)i;
         ++g.live_edges;
     }
-    uint64_t nsq = r.u64();
-    if (!r.ok) return false;
-    for (uint64_t i = 0; i < nsq && r.ok; ++i) {
-        uint64_t nl = r.u64();
-        if (!r.need(nl)) return false;
+    const uint64_t nsq = r.u64();
+    if (!r.ok || nsq > left() / 12) return false;  // a sequence is at least 12 bytes
+    for (uint64_t i = 0; i < nsq; ++i) {
+        const uint64_t nl = r.u64();
+        if (!r.ok || nl > left()) return false;
         std::string name((const char *)r.p, nl);
         r.p += nl;
-        g.sequences.push_back({name, r.u32()});
+        const uint32_t first = r.u32();
+        if (!r.ok || first >= nn) return false;
+        g.sequences.push_back({std::move(name), first});
     }
-    uint64_t nt = r.u64();
-    if (!r.ok || nt > nn) return false;
-    for (uint64_t i = 0; i < nt; ++i) g.topological_sorted.push_back(r.u32());
+    const uint64_t nt = r.u64();
+    if (!r.ok || nt > left() / 4 || (nt != 0 && nt != nn)) return false;
+    std::vector<uint32_t> file_order;
+    for (uint64_t i = 0; i < nt; ++i) file_order.push_back(r.u32());
     g.start_node = r.u32();
     g.end_node = r.u32();
-    return r.ok;
+    if (!r.ok || g.start_node >= nn || g.end_node >= nn || g.start_node == g.end_node) return false;
+    if (nt) {
+        // a permutation that respects every edge: anything else would index out of bounds (or misorder the DP rows) later
+        std::vector<uint32_t> rank(nn, NIL);
+        for (uint64_t i = 0; i < nt; ++i) {
+            if (file_order[i] >= nn || rank[file_order[i]] != NIL) return false;
+            rank[file_order[i]] = (uint32_t)i;
+        }
+        for (const auto &e : g.edges)
+            if (!e.vacant && rank[e.node[0]] >= rank[e.node[1]]) return false;
+        g.topological_sorted = std::move(file_order);
+    }
+    return true;
 }
 
 }  // namespace poasta

@@ -63,14 +63,11 @@ class POAGraph:
     # -- graphs/poa.rs:171-321 --
     def add_alignment_with_weights(self, name, seq, alignment=None, weights=None):
         seq = bytes(seq)
-        if weights is not None and len(weights) != len(seq):
-            from .errors import WeightsUnequalSize
-            raise WeightsUnequalSize(f"{len(seq)} != {len(weights)}")
-        w = None
+        w, wn = None, 0
         if weights is not None:
-            w = (C.c_uint64 * len(weights))(*weights)
+            w, wn = (C.c_uint64 * max(1, len(weights)))(*weights), len(weights)  # the C side checks the length (poa.rs:178-180)
         if alignment is None:
-            rc = self._lib.poasta_graph_add_alignment(self._h, name.encode(), seq, len(seq), None, None, 0, w)
+            rc = self._lib.poasta_graph_add_alignment(self._h, name.encode(), seq, len(seq), None, None, 0, w, wn)
         else:
             r, q = _pairs_to_arrays(alignment) if not isinstance(alignment, tuple) else alignment
             r = np.ascontiguousarray(r, dtype=np.uint32)
@@ -84,13 +81,14 @@ class POAGraph:
             else:
                 n = len(r)
             rc = self._lib.poasta_graph_add_alignment(self._h, name.encode(), seq, len(seq),
-                                                      r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), n, w)
+                                                      r.ctypes.data_as(u32p), q.ctypes.data_as(u32p), n, w, wn)
         check(rc, "add_alignment_with_weights")
 
     def get_aligned_nodes(self, node):
-        buf = (C.c_uint32 * 64)()
-        n = self._lib.poasta_graph_aligned_nodes(self._h, node, buf, 64)
-        return list(buf[:min(n, 64)])
+        n = self._lib.poasta_graph_aligned_nodes(self._h, node, None, 0)  # the call returns the full count
+        buf = (C.c_uint32 * max(1, n))()
+        self._lib.poasta_graph_aligned_nodes(self._h, node, buf, n)
+        return list(buf[:n])
 
     # -- flattened AlignableRefGraph --
     def view(self):

@@ -223,3 +223,29 @@ def test_msa_reproduces_committed_golden_outputs(name):
     assert graphs[0].to_fasta() == open(f"tests/golden/{name}.expected.fa", "rb").read()
     assert graphs[0].to_gfa() == open(f"tests/golden/{name}.expected.gfa", "rb").read()
     assert [int(s) for s in scores[0]] == [int(x) for x in open(f"tests/golden/{name}.expected.scores").read().split()]
+
+
+def test_dp_mode_many_short_queries_are_chunked_not_overallocated():
+    """the DP chunk budget must count what the chosen kernel allocates (the warp kernel's bit planes cost 1 KB per
+    row whatever the query length). Many short queries against a 3k-node graph with a small budget: split into chunks, all right."""
+    import subprocess, sys, os
+    code = '''
+import sys
+sys.path[:0] = ["tests", "."]
+import helpers as H
+from poasta_b200 import POAGraph, TIEBREAK_DP, align_batch, synth
+g = POAGraph()
+for n, s in synth.parse_fasta(synth.family(11, 3, 3000, 0.02)):
+    if g.is_empty():
+        g.add_alignment_with_weights(n, s, None)
+    else:
+        g.add_alignment_with_weights(n, s, H.oracle_align(g, s)[2])
+qs = [synth.parse_fasta(synth.family(100 + i, 1, 40, 0.0))[0][1] for i in range(600)] + [b""]
+res = align_batch([g], qs, [0] * len(qs), tiebreak=TIEBREAK_DP)
+bad = sum(r.score != H.oracle_align(g, q)[1] for q, r in list(zip(qs, res))[::25] + [(qs[-1], res[-1])])
+assert res[-1].alignment == []
+print("BAD", bad)
+'''
+    env = dict(os.environ, POASTA_DP_BUDGET_MB="64")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "BAD 0" in r.stdout, r.stdout + r.stderr[-1500:]

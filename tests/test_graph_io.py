@@ -173,3 +173,64 @@ def test_roundtrips_on_progressive_graphs():
         assert g4.to_fasta() == msa and g4.num_sequences() == g.num_sequences()
         n += 1
     assert n == 16
+
+
+def test_malformed_poasta_files_are_rejected_not_trusted():
+    """`view`, `stats` and `align -I` read untrusted files: truncations and corrupted ids / counts must give an error status,
+    never an out-of-bounds access, a huge allocation or an exception across the C boundary."""
+    import random
+    import struct
+    from poasta_b200 import POAGraph, synth
+    import helpers as H
+    rc, blob, _, _ = H.oracle_msa(synth.family(5, 6, 80, 0.1), fmt=3)
+    assert rc == 0
+    g = POAGraph.load(blob)
+    assert g.save() == blob
+    rng = random.Random(7)
+    # every truncation point in the header and a sample of the rest
+    for cut in list(range(0, 64)) + [rng.randrange(len(blob)) for _ in range(300)]:
+        with pytest.raises(OSError):
+            POAGraph.load(blob[:cut])
+    # counts blown up: node count, an aligned-nodes count, the edge count
+    for off, val in ((4, 1 << 40), (4, (1 << 31) - 1), (4 + 8 + 1, 1 << 33)):
+        bad = bytearray(blob)
+        bad[off:off + 8] = struct.pack("<Q", val)
+        with pytest.raises(OSError):
+            POAGraph.load(bytes(bad))
+    # random single-word corruptions: either rejected, or a graph whose every id is in range (all writers must run)
+    accepted = 0
+    for _ in range(400):
+        bad = bytearray(blob)
+        off = rng.randrange(4, len(bad) - 4)
+        bad[off:off + 4] = struct.pack("<I", rng.choice([0xFFFFFFFF, 0x7FFFFFFF, len(blob), rng.randrange(1 << 32)]))
+        try:
+            h = POAGraph.load(bytes(bad))
+        except OSError:
+            continue
+        accepted += 1
+        h.view_arrays()
+        for fn in (h.to_fasta, h.to_gfa, h.save):
+            try:
+                fn()
+            except OSError:
+                pass
+    assert accepted < 400
+
+
+def test_add_alignment_argument_checks():
+    from poasta_b200 import AlignedPair, InvalidAlignment, POAGraph, WeightsUnequalSize
+    g = POAGraph()
+    g.add_alignment_with_weights("a", b"ACGT", None, weights=[1, 1, 1, 1])
+    with pytest.raises(WeightsUnequalSize):  # poa.rs:178-180, checked behind the C boundary
+        g.add_alignment_with_weights("b", b"ACGT", None, weights=[1, 1, 1])
+    with pytest.raises(InvalidAlignment):  # node id out of range: the reference panics on graph[rpos]
+        g.add_alignment_with_weights("c", b"AC", [AlignedPair(999, 0), AlignedPair(3, 1)])
+    with pytest.raises(InvalidAlignment):  # query position out of range: the reference panics on sequence[qpos]
+        g.add_alignment_with_weights("d", b"AC", [AlignedPair(2, 0), AlignedPair(3, 7)])
+    assert g.num_sequences() == 1
+    # a column of more than 64 mutually aligned nodes is reported in full
+    h = POAGraph()
+    h.add_alignment_with_weights("s0", bytes([33]), None)
+    for k in range(1, 80):
+        h.add_alignment_with_weights(f"s{k}", bytes([33 + k]), [AlignedPair(2, 0)])
+    assert len(h.get_aligned_nodes(2)) == 79

@@ -4,7 +4,7 @@
 // with the path of the A* restatement and classify the first divergence; then evaluate on-device
 // detectors that would let an alignment skip the order-exact search.
 //
-//   g++ -O2 -std=c++17 -o /tmp/tie_study tools/tie_study.cpp poasta_b200/csrc/synth.c && /tmp/tie_study 200 1000 0.05 20
+//   g++ -O2 -std=c++17 -o /tmp/tie_study tools/tie_study.cpp -x c poasta_b200/csrc/synth.c && /tmp/tie_study 60 1000 0.05 20
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -13,8 +13,7 @@
 
 #include "../oracle/astar_oracle.hpp"
 #include "../oracle/dp_model.hpp"
-#include "../poasta_b200/csrc/flatten.hpp"
-#include "../poasta_b200/csrc/poa_io.hpp"
+#include "../oracle/poa_oracle.hpp"
 
 extern "C" size_t synth_family(uint64_t seed, uint32_t n_seqs, uint32_t root_len, double rate, const char *prefix, char *out,
                                size_t cap);
@@ -86,18 +85,18 @@ int main(int argc, char **argv) {
     Counters c;
     for (uint32_t f = 0; f < nfam; ++f) {
         size_t len = synth_family(0xC200000000ull + f, nseq, L, rate, "f", buf.data(), buf.size());
-        auto recs = poasta::parse_fasta(buf.data(), len);
-        poasta::POAGraph g;
-        poasta::FlatGraph flat;
+        auto recs = poa::read_fasta(buf.data(), len);
+        poa::POAGraph g;
         for (size_t i = 0; i < recs.size(); ++i) {
             const uint8_t *s = (const uint8_t *)recs[i].seq.data();
             const uint32_t Q = (uint32_t)recs[i].seq.size();
+            const std::vector<uint64_t> ones(Q, 1);
             if (g.is_empty()) {
-                g.add_alignment_with_weights(recs[i].name, s, Q, false, nullptr, 0);
+                g.add_alignment_with_weights(recs[i].name, recs[i].seq, nullptr, ones);
                 continue;
             }
-            flat.build(g);
-            poasta_graph_view view = flat.view();
+            const poa::Flat flat(g);
+            poasta_graph_view view = flat.view;
             AlignOptions opt;
             std::vector<uint32_t> dump, pruned, pops;
             opt.dump = &dump;
@@ -233,9 +232,9 @@ int main(int argc, char **argv) {
                 c.pass_det_same[d] += det_ok[d] && same;
             }
 
-            std::vector<poasta::AlignedPair> aln(r.rpos.size());
+            std::vector<poa::Pair> aln(r.rpos.size());
             for (size_t k = 0; k < aln.size(); ++k) aln[k] = {r.rpos[k], r.qpos[k]};
-            g.add_alignment_with_weights(recs[i].name, s, Q, true, aln.data(), aln.size());
+            g.add_alignment_with_weights(recs[i].name, recs[i].seq, &aln, ones);
         }
     }
     printf("alignments %lu  same_score %lu  same_path %lu (%.1f%%)\n", c.n, c.same_score, c.same_path, 100.0 * c.same_path / c.n);
