@@ -85,7 +85,7 @@ CONFIGS = {
             what="synthetic gene families x 20 seqs x 1 kb, 5% subs+indels, global, costs 4/6/2, mingap; progressive MSA (19 rounds)"),
     3: dict(name="config3", seqs=30, length=500, rate=0.10, units=12000, unit="windows",
             what="long-read consensus windows x 30 reads x 500 bp, 10% error, global, costs 4/6/2, mingap; progressive MSA (29 rounds)"),
-    4: dict(name="config4", seqs=40, length=1500, rate=0.15, units=1, unit="family",
+    4: dict(name="config4", seqs=16, length=1500, rate=0.15, units=1, unit="family",
             what="ONE family of 16S-like 1.5 kb sequences at 15% divergence (a single sequential chain: latency-bound, replicas only); "
                  "bounded to the first `seqs` members of the 1,000"),
     5: dict(name="config5", seqs=50, length=20000, rate=0.01, units=20000, unit="reads", read_len=2000, read_rate=0.05,

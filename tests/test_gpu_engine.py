@@ -122,10 +122,10 @@ def test_32_bit_score_cells():
 
 
 def test_config2_scale_sample():
-    # 1/10-scale slice of config 2 through the engine; every 40th family checked against the oracle (scores, FASTA, GFA)
+    # 1/10-scale slice of config 2 through the engine; every 50th family checked against the oracle (scores, FASTA, GFA)
     fastas = [synth.config2_family(f) for f in range(1000)]
     graphs, scores, cells = msa_batch(fastas)
-    for f in range(0, 1000, 40):
+    for f in range(0, 1000, 50):
         out, osc = _expect(fastas[f])
         assert list(scores[f]) == osc and graphs[f].to_fasta() == out
         assert graphs[f].to_gfa() == _expect(fastas[f], fmt=1)[0]
@@ -138,10 +138,10 @@ def test_config2_scale_sample():
 
 
 def test_config3_scale_sample():
-    # 2,000 windows x 30 reads x 500 bp at 10 % error (1/100 of config 3, full window size); every 100th checked
+    # 2,000 windows x 30 reads x 500 bp at 10 % error (1/100 of config 3, full window size); every 125th checked
     fastas = [synth.config3_window(w) for w in range(2000)]
     graphs, scores, cells = msa_batch(fastas)
-    for w in range(0, 2000, 100):
+    for w in range(0, 2000, 125):
         out, osc = _expect(fastas[w])
         assert list(scores[w]) == osc and graphs[w].to_fasta() == out
 

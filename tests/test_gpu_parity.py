@@ -242,8 +242,14 @@ for n, s in synth.parse_fasta(synth.family(11, 3, 3000, 0.02)):
         g.add_alignment_with_weights(n, s, H.oracle_align(g, s)[2])
 qs = [synth.parse_fasta(synth.family(100 + i, 1, 40, 0.0))[0][1] for i in range(600)] + [b""]
 res = align_batch([g], qs, [0] * len(qs), tiebreak=TIEBREAK_DP)
-bad = sum(r.score != H.oracle_align(g, q)[1] for q, r in list(zip(qs, res))[::25] + [(qs[-1], res[-1])])
-assert res[-1].alignment == []
+# DP mode returns the optimum and the dense model's alignment (the reference's own search may sit above the optimum for a
+# 40-base query against a 3 kb graph); the empty query goes through the search kernel and equals the reference
+bad = 0
+for q, r in list(zip(qs, res))[:600:25]:
+    sc, pairs, _ = H.dpmodel_align(g, q)
+    bad += not (r.score == sc and r.alignment == pairs)
+st, sc, pairs, _ = H.oracle_align(g, b"")
+bad += not (res[-1].score == sc and res[-1].alignment == pairs == [])
 print("BAD", bad)
 '''
     env = dict(os.environ, POASTA_DP_BUDGET_MB="64")
