@@ -772,7 +772,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     // u16 score cells when no reachable score can hit 0xFFFF (all nodes deleted + all query bases inserted is the worst case)
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
-    const bool cell16 = worst < 0x7F00u;  // the top bit of a cell is the reached mark
+    const bool cell16 = worst < replay::CELL16_LIMIT;
     const uint64_t plane_bytes = up(4 * cells_per_aln * (cell16 ? 2 : 4));  // records {M, D, I, epoch}
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
@@ -784,16 +784,17 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs
     static const double slab_fraction = getenv("POASTA_SLAB_FRACTION") ? atof(getenv("POASTA_SLAB_FRACTION")) : 0.6;
     const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(slab_fraction * (double)total_b)) / tl_lane_count;
-    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_dfa = 0;
+    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_bits = 0, off_dfa = 0;
     off_qhead = SLAB_CELLS + plane_bytes;
     off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
     off_free = off_items + up(max_items * 16);
     off_reached = off_free + up(max_items * 4);                   // reached bounds: 2 words per node
-    off_dfa = off_reached + up((uint64_t)pr.max_V * 8);
+    off_bits = off_reached + up((uint64_t)pr.max_V * 8);          // reached-offset bitmap: Wb words per node
+    off_dfa = off_bits + up((uint64_t)pr.max_V * ((dmax.W + 31) / 32) * 4);
     slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);           // DFA frames: 6 words
-    const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 64);
+    const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 32);  // 32 CTAs of one warp per SM
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
-    const unsigned warps_per_cta = workers > (uint64_t)c.n_sms * 24 ? 2 : 1;  // at most 32 CTAs are resident per SM
+    const unsigned warps_per_cta = 1;  // one warp per CTA (replay_kernel.cuh)
     workers = ((workers + warps_per_cta - 1) / warps_per_cta) * warps_per_cta;
     if (!c.r_slabs.reserve(workers * slab)) {
         workers = warps_per_cta;
@@ -845,7 +846,7 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.prm = replay::Params{prm.mismatch, prm.gap_open, prm.gap_extend, prm.mode, prm.heuristic};
     B.slabs = (uint8_t *)c.r_slabs.d;
     B.slab_bytes = slab;
-    B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_dfa = off_dfa;
+    B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_bits = off_bits, B.off_dfa = off_dfa;
     B.max_items = (uint32_t)max_items;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;
@@ -861,15 +862,12 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
 
     CK(cudaEventRecord(c.ev0, s));
     {
-        // MINB = resident CTAs per SM the register allocation must allow: 16 -> 64 registers, no spills, 32 warps per SM
-        static const int minb = getenv("POASTA_REPLAY_MINB") ? atoi(getenv("POASTA_REPLAY_MINB")) : 16;
-        const dim3 grid((unsigned)(workers / warps_per_cta)), block(warps_per_cta * 32);
+        // 32 resident one-warp CTAs per SM -> 64 registers, 32 workers per SM (replay_kernel.cuh)
+        const dim3 grid((unsigned)workers), block(32);
         auto launch = [&](auto cell, auto heur) {
             using CellT = decltype(cell);
             constexpr int H = decltype(heur)::value;
-            if (minb >= 24) replay_kernel<CellT, 24, H><<<grid, block, 0, s>>>(B);
-            else if (minb >= 16) replay_kernel<CellT, 16, H><<<grid, block, 0, s>>>(B);
-            else replay_kernel<CellT, 14, H><<<grid, block, 0, s>>>(B);
+            replay_kernel<CellT, 32, H><<<grid, block, 0, s>>>(B);
         };
         auto launch_cell = [&](auto cell) {
             if (prm.heuristic == 0) launch(cell, std::integral_constant<int, 0>{});

@@ -41,7 +41,7 @@ struct EngineDev {
     uint32_t *counters;   // [0] next ticket to consume, [1] next ticket to fill, [2] suspended families
     uint32_t *suspended;  // family ids
     uint8_t *workers;
-    uint64_t worker_bytes, cell_bytes, off_qhead, off_items, off_free, off_rb, off_dfa, off_pairs, off_index;
+    uint64_t worker_bytes, cell_bytes, off_qhead, off_items, off_free, off_rb, off_bits, off_dfa, off_pairs, off_index;
     uint32_t max_items, pair_cap, f_cap;
     dg::IndexCaps icap;
     replay::Params prm;
@@ -78,14 +78,15 @@ __device__ __noinline__ int engine_first(dg::Store &g, const uint8_t *q, uint32_
 
 enum : int { ENG_CONTINUE = 0, ENG_FAILED = 1, ENG_SUSPEND = 2 };
 
-// 16 resident CTAs of 2 warps per SM -> 64 registers, 32 workers per SM. Measured alternatives (profiles/README.md, round 2):
+// 32 resident CTAs of 1 warp per SM -> 64 registers, 32 workers per SM. Measured alternatives (profiles/README.md, round 2):
 // 40 registers / 48 workers per SM: 18.2k instead of 13.5k cycles per visited state, 26 % slower at 7,104 families.
 template <typename CellT, int HEUR>
-__global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_kernel(EngineDev E) {
-    __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + wib;
-    uint8_t *slab = E.workers + (uint64_t)worker * E.worker_bytes;
+__global__ void __launch_bounds__(32, 32) msa_engine_kernel(EngineDev E) {
+    __shared__ uint32_t s_qwin[replay::QWIN * 3];
+    __shared__ replay::Scratch s_scr;  // the worker's pointer blocks at fixed shared-memory addresses (see replay_kernel.cuh)
+    __shared__ replay::Graph s_gr;
+    const uint32_t lane = threadIdx.x;
+    uint8_t *slab = E.workers + (uint64_t)blockIdx.x * E.worker_bytes;
     for (;;) {
         uint32_t h = 0;
         if (lane == 0) h = atomicAdd(&E.counters[0], 1u);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
             const uint64_t m = E.prm.x > E.prm.o + E.prm.e ? E.prm.x : E.prm.o + E.prm.e;
             const uint64_t worst = ((uint64_t)V + Q + 4) * m + E.prm.o;  // every node deleted + every base inserted
             const bool fits = V <= E.icap.V && F->live_edges <= E.icap.E && (uint64_t)V * dims.W * sizeof(replay::Rec<CellT>) <= E.cell_bytes &&
-                              dims.f_max <= E.f_cap && V + Q + 2 <= E.pair_cap && (sizeof(CellT) == 4 || worst < 0x7F00u);
+                              dims.f_max <= E.f_cap && V + Q + 2 <= E.pair_cap && (sizeof(CellT) == 4 || worst < replay::CELL16_LIMIT);
             if (!fits) {
                 outcome = ENG_SUSPEND;
             } else {
@@ -126,26 +127,28 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
                 if (engine_build_index(g, w, HEUR == 2, lane) != dg::DG_OK) {
                     outcome = ENG_SUSPEND;
                 } else {
-                    const uint32_t epoch = worker_begin_alignment<CellT>(slab, E.cell_bytes, E.off_qhead, E.off_rb, V, s_qwin[wib], lane);
-                    {
-                        replay::Graph rg;
+                    const uint32_t Wb = (dims.W + 31) / 32;
+                    const uint32_t epoch = worker_begin_alignment<CellT>(slab, E.cell_bytes, E.off_qhead, E.off_rb, E.off_bits, V, Wb, s_qwin, lane);
+                    if (lane == 0) {
+                        replay::Graph &rg = s_gr;
                         rg.V = V, rg.start = dg::Store::START, rg.end = dg::Store::END;
                         rg.nodes = w.nodes, rg.succ = w.succ, rg.pred = w.pred, rg.bub = w.bub;
                         rg.path_off = w.path_off, rg.path_rem = w.path_rem;
-                        replay::Scratch s;
+                        replay::Scratch &s = s_scr;
                         s.planes = slab + SLAB_CELLS;
                         s.epoch = epoch;
                         s.qhead = reinterpret_cast<uint32_t *>(slab + E.off_qhead);
-                        s.qwin = s_qwin[wib];
+                        s.qwin = s_qwin;
                         s.items = reinterpret_cast<replay::Item *>(slab + E.off_items);
                         s.free_slots = reinterpret_cast<uint32_t *>(slab + E.off_free);
                         s.rb = reinterpret_cast<uint32_t *>(slab + E.off_rb);
+                        s.rbits = reinterpret_cast<uint32_t *>(slab + E.off_bits);
+                        s.Wb = Wb;
                         s.dfa = reinterpret_cast<uint32_t *>(slab + E.off_dfa);
                         s.W = dims.W, s.f_max = dims.f_max;
                         s.max_items = E.max_items;
                         uint32_t *pr = reinterpret_cast<uint32_t *>(slab + E.off_pairs), *pq = pr + E.pair_cap;
                         replay::Search<CellT, HEUR> search(rg, q, Q, E.prm, s);
-                        if (lane == 0) {
                         const long long t_search = clock64();
                         const replay::Result r = search.run(pr, pq, E.pair_cap);
                         out[6] = (uint32_t)((clock64() - t_search) >> 10);
@@ -163,7 +166,6 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, 16) msa_engine_
                                     outcome = ENG_FAILED, fam_status = rc == dg::DG_CAPACITY ? POASTA_ERR_UNSUPPORTED : POASTA_ERR_INVALID_ALIGNMENT;
                             }
                             out[1] = (uint32_t)fam_status;
-                        }
                         }
                     }
                     outcome = __shfl_sync(0xFFFFFFFFu, outcome, 0);

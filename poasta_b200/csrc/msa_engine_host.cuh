@@ -24,7 +24,7 @@ struct EngineStats {
 
 // worker scratch layout for given capacities
 struct WorkerLayout {
-    uint64_t cell_bytes, off_qhead, off_items, off_free, off_rb, off_dfa, off_pairs, off_index, total;
+    uint64_t cell_bytes, off_qhead, off_items, off_free, off_rb, off_bits, off_dfa, off_pairs, off_index, total;
     uint32_t max_items, pair_cap, f_cap;
     dg::IndexCaps icap;
     WorkerLayout(uint32_t Vw, uint32_t Qmax, bool cell16, bool full_items, const poasta_params &prm) {
@@ -40,7 +40,8 @@ struct WorkerLayout {
         off_items = off_qhead + up((uint64_t)f_cap * 12);
         off_free = off_items + up((uint64_t)max_items * 16);
         off_rb = off_free + up((uint64_t)max_items * 4);
-        off_dfa = off_rb + up((uint64_t)Vw * 8);
+        off_bits = off_rb + up((uint64_t)Vw * 8);
+        off_dfa = off_bits + up((uint64_t)Vw * ((d.W + 31) / 32) * 4);
         off_pairs = off_dfa + up((uint64_t)(Vw + 2) * 24);
         off_index = off_pairs + up((uint64_t)pair_cap * 8);
         total = off_index + up(dg::IndexLayout(icap).total);
@@ -145,8 +146,8 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
         for (uint32_t i = 0; i < nf; ++i) todo[i] = i;
         std::vector<uint32_t> left(nf);
         for (uint32_t i = 0; i < nf; ++i) left[i] = hf[i].n_seqs;
-        // largest V a 16-bit table can carry: (V + Q + 4) * m + o < 0x7F00
-        const uint64_t v16 = 0x7F00u > prm.gap_open ? (0x7F00u - 1 - prm.gap_open) / std::max<uint64_t>(m, 1) : 0;
+        // largest V a 16-bit table can carry: (V + Q + 4) * m + o < CELL16_LIMIT
+        const uint64_t v16 = replay::CELL16_LIMIT > prm.gap_open ? (replay::CELL16_LIMIT - 1 - prm.gap_open) / std::max<uint64_t>(m, 1) : 0;
         const uint64_t Vmax16 = v16 > (uint64_t)Qmax + 4 ? v16 - Qmax - 4 : 0;
         uint64_t Vw = std::min<uint64_t>(Vworst, std::max<uint64_t>((uint64_t)V0max + 2 * (uint64_t)Qmax + 64, 256));
         bool full_items = false;
@@ -167,7 +168,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             }
             WorkerLayout L((uint32_t)Vw, Qmax, cell16, full_items, prm);
             uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want, worker_budget / L.total));
-            const unsigned wpc = workers > (uint64_t)c.n_sms * 16 ? 2 : 1;  // at most 32 CTAs are resident per SM
+            const unsigned wpc = 1;  // one warp per CTA (replay_kernel.cuh)
             workers = (workers + wpc - 1) / wpc * wpc;
             if (!eb.workers.reserve(workers * L.total)) {
                 workers = wpc;
@@ -202,7 +203,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             E.suspended = (uint32_t *)eb.suspended.d;
             E.workers = (uint8_t *)eb.workers.d;
             E.worker_bytes = L.total, E.cell_bytes = L.cell_bytes;
-            E.off_qhead = L.off_qhead, E.off_items = L.off_items, E.off_free = L.off_free, E.off_rb = L.off_rb, E.off_dfa = L.off_dfa;
+            E.off_qhead = L.off_qhead, E.off_items = L.off_items, E.off_free = L.off_free, E.off_rb = L.off_rb, E.off_bits = L.off_bits, E.off_dfa = L.off_dfa;
             E.off_pairs = L.off_pairs, E.off_index = L.off_index;
             E.max_items = L.max_items, E.pair_cap = L.pair_cap, E.f_cap = L.f_cap;
             E.icap = L.icap;

@@ -127,13 +127,16 @@ struct alignas(16) Item {
 };
 
 struct Scratch {  // one slab per in-flight alignment
-    void *planes;          // V * W records Rec<CellT> {M, D, I, epoch}; cell = score | reached-flag (top bit, Match only); all-ones-but-top = unvisited
+    void *planes;          // V * W records Rec<CellT> {M, D, I, epoch}; cell = score, all-ones = unvisited
     uint32_t epoch;        // epoch of this alignment (1 .. CellT max); records stamped otherwise read as unvisited
     uint32_t *qhead;       // f_max * 3 stack heads (0 = empty, else item index + 1) - authoritative outside the window
     uint32_t *qwin;        // QWIN * 3 heads of priorities [win_base, win_base + QWIN): shared memory on the device
     Item *items;           // max_items (multiple of CHUNK), chunk c = slots [8 c, 8 c + 8)
     uint32_t *free_slots;  // max_items / CHUNK: stack of recycled chunks (its top stays cache-hot, unlike a list threaded through items)
     uint32_t *rb;          // per node [lo, hi + 1] of the reached offsets (hi + 1 == 0: none)
+    uint32_t *rbits;       // per node Wb words: bit o = offset o is a reached offset of this (exit) node - the reference's
+                           // BTreeSet<offset> per bubble exit (gap_affine.rs:711, 767-773); cleared per alignment
+    uint32_t Wb;           // words per bitmap row = (W + 31) / 32
     uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
     uint32_t W, max_items, f_max;
 };
@@ -153,15 +156,31 @@ struct Result {
 
 template <typename CellT> struct CellTraits;
 // CHECK_WRAP: the reference's NonMaxU32 arithmetic panics when a score reaches u32::MAX. The host picks 16-bit cells only
-// when every reachable score stays below 0x7F00, so that instantiation needs none of those tests in its hot loop.
+// when every reachable score stays below CELL16_LIMIT, so that instantiation needs none of those tests in its hot loop.
 template <> struct CellTraits<uint16_t> {
-    static constexpr uint16_t FLAG = 0x8000u, CUNV = 0x7FFFu;
+    static constexpr uint16_t CUNV = 0xFFFFu;
     static constexpr bool CHECK_WRAP = false;
 };
 template <> struct CellTraits<uint32_t> {
-    static constexpr uint32_t FLAG = 0x80000000u, CUNV = 0x7FFFFFFFu;
+    static constexpr uint32_t CUNV = 0xFFFFFFFFu;
     static constexpr bool CHECK_WRAP = true;
 };
+constexpr uint32_t CELL16_LIMIT = 0xFF00u;  // 16-bit cells are picked only when no reachable score can get here
+
+RP_HD uint32_t rp_clz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)x);
+#else
+    return (uint32_t)__builtin_clz(x);
+#endif
+}
+RP_HD uint32_t rp_ctz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
 
 // ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) -----------------------------------------------
 // Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped (the reference would panic).
@@ -169,15 +188,15 @@ template <typename CellT>
 struct PruneCtx {
     const Rec<CellT> *table;  // the visited table; record of (node, off) at node * W + off
     const uint32_t *rb;       // reached bounds per node
-    uint32_t W, Q, o, e;
-    CellT epoch;
+    const uint32_t *rbits;    // reached-offset bitmap, Wb words per node
+    uint32_t W, Wb, Q, o, e;
 };
 
 // can_improve_bubble for one bubble; true = the state can still improve on it (no prune from this bubble)
 template <typename CellT>
 RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, uint32_t off, uint32_t st, uint32_t score,
                         bool &wrapped) {
-    constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
+    constexpr CellT CUNV = CellTraits<CellT>::CUNV;
     RP_CNT(C_PRUNE_BUB);
     if (node == b.exit || off + b.max_d > c.Q) return true;
     const uint32_t lo = c.rb[2 * (size_t)b.exit], hi1 = c.rb[2 * (size_t)b.exit + 1], mde = b.mde;
@@ -188,31 +207,37 @@ RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, 
     auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
     const uint32_t tmin = off + b.min_d, tmax = off + b.max_d;
     const Rec<CellT> *mrow = c.table + (size_t)b.exit * c.W;
-    auto at = [&](uint32_t i) -> CellT {  // Match cell of the exit row
-        RP_CNT(C_PRUNE_PROBE);
-        const Rec<CellT> r = mrow[i];
-        return r.ep == c.epoch ? r.m : CUNV;
-    };
-    // reached offsets = Match cells of the exit row with the flag bit; scans stay inside [lo, hi]
+    const uint32_t *bits = c.rbits + (size_t)b.exit * c.Wb;
+    // reached offsets = set bits of the exit's bitmap row, all inside [lo, hi1): a range query is one or two word operations
+    // (round 1 scanned the Match cells one by one: ~10 dependent probes per visited state)
     auto prev_of = [&](uint32_t lim) -> uint32_t {  // largest reached offset < lim
         if (lim <= lo) return UNV;
-        uint32_t i = lim > hi1 ? hi1 - 1 : lim - 1;
+        const uint32_t i = (lim > hi1 ? hi1 : lim) - 1, wlo = lo >> 5;
+        uint32_t w = i >> 5;
+        RP_CNT(C_PRUNE_PROBE);
+        uint32_t word = bits[w] & (0xFFFFFFFFu >> (31 - (i & 31)));
         for (;;) {
-            if (at(i) & FLAG) return i;
-            if (i == lo) return UNV;
-            --i;
+            if (word) return w * 32 + 31 - rp_clz(word);
+            if (w == wlo) return UNV;
+            RP_CNT(C_PRUNE_PROBE);
+            word = bits[--w];
         }
     };
     auto next_of = [&](uint32_t lim) -> uint32_t {  // smallest reached offset >= lim
         if (lim >= hi1) return UNV;
-        uint32_t i = lim < lo ? lo : lim;
+        const uint32_t i = lim < lo ? lo : lim, whi = (hi1 - 1) >> 5;
+        uint32_t w = i >> 5;
+        RP_CNT(C_PRUNE_PROBE);
+        uint32_t word = bits[w] & (0xFFFFFFFFu << (i & 31));
         for (;;) {
-            if (at(i) & FLAG) return i;
-            if (++i >= hi1) return UNV;
+            if (word) return w * 32 + rp_ctz(word);
+            if (w == whi) return UNV;
+            RP_CNT(C_PRUNE_PROBE);
+            word = bits[++w];
         }
     };
     auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
-        const CellT v = (CellT)(at(r) & (CellT)~FLAG);
+        const CellT v = mrow[r].m;  // a reached offset was written by THIS alignment: no epoch test
         RP_CNT(C_PRUNE_SCORE);
         const uint32_t t = (uint32_t)v + plus;
         if (CellTraits<CellT>::CHECK_WRAP && (v == CUNV || t == UNV)) wrapped = true;
@@ -274,12 +299,12 @@ RP_HD int prune_eval(const PruneCtx<CellT> &c, const BubQ *bubs, uint32_t n_bub,
 }
 
 // CellT = uint16_t halves the table footprint (more alignments in flight); the host picks it only when the largest
-// possible score (every node deleted + every query base inserted) is below 0x7F00.
+// possible score (every node deleted + every query base inserted) is below CELL16_LIMIT.
 // HEUR = Params::heuristic as a compile-time constant: every push evaluates h(), and the three heuristics inlined at every
 // push site tripled the kernel's code size (instruction-cache misses were 20-30 % of its stall cycles).
 template <typename CellT, int HEUR>
 struct Search {
-    static constexpr CellT FLAG = CellTraits<CellT>::FLAG, CUNV = CellTraits<CellT>::CUNV;
+    static constexpr CellT CUNV = CellTraits<CellT>::CUNV;
     static constexpr bool CHECK_WRAP = CellTraits<CellT>::CHECK_WRAP;
     const Graph &g;
     const uint8_t *q;
@@ -321,7 +346,7 @@ struct Search {
         else r.i = v;
     }
     RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
-        const CellT v = (CellT)(field(load(rec_ptr(node, off)), st) & (CellT)~FLAG);
+        const CellT v = field(load(rec_ptr(node, off)), st);
         return v == CUNV ? UNV : (uint32_t)v;
     }
     RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
@@ -336,12 +361,11 @@ struct Search {
             err = RP_SCORE_WRAP;
             return false;
         }
-        const CellT cur = field(r, st);
-        const CellT curv = (CellT)(cur & (CellT)~FLAG);
+        const CellT curv = field(r, st);
         RP_CNT(C_RELAX);
-        if (curv == CUNV || v < (uint32_t)curv) {
+        if (v < (uint32_t)curv) {  // unvisited = all ones: greater than any score
             RP_CNT(C_RELAX_OK);
-            set_field(r, st, (CellT)((CellT)v | (CellT)(cur & FLAG)));  // a reached offset stays reached when its score improves
+            set_field(r, st, (CellT)v);
             *ptr = r;
             return true;
         }
@@ -485,10 +509,7 @@ struct Search {
     // ---- reached marks (BTreeSet<offset> per exit; gap_affine.rs:767-773) -------------------------------
     RP_HD void mark_reached(uint32_t node, bool is_exit, uint32_t off, uint32_t st) {
         if (st == ST_M && is_exit) {
-            R *ptr = rec_ptr(node, off);
-            R r = load(ptr);
-            r.m |= FLAG;
-            *ptr = r;
+            s.rbits[(size_t)node * s.Wb + (off >> 5)] |= 1u << (off & 31);
             uint32_t *b = s.rb + 2 * (size_t)node;
             if (b[1] == 0) {
                 b[0] = off, b[1] = off + 1;
@@ -504,7 +525,7 @@ struct Search {
         if (nb == 0) return false;
         RP_T0;
         RP_CNT(C_PRUNE_CALL);
-        const PruneCtx<CellT> c{static_cast<const R *>(s.planes), s.rb, s.W, Q, p.o, p.e, (CellT)s.epoch};
+        const PruneCtx<CellT> c{static_cast<const R *>(s.planes), s.rb, s.rbits, s.W, s.Wb, Q, p.o, p.e};
         const int r = prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
         RP_ACC(prof_prune);
@@ -600,8 +621,7 @@ struct Search {
             const NodeB nb = node_b(it.node);
             const uint32_t n_succ = na.counts & 0xFFFF;
             {
-                const CellT ownv = (CellT)(own & (CellT)~FLAG);
-                if (ownv != CUNV && it.score > (uint32_t)ownv) {
+                if (it.score > (uint32_t)own) {  // unvisited (all ones) never compares below a score
                     RP_CNT(C_POP_STALE);
                     continue;
                 }

@@ -28,14 +28,18 @@ struct ReplayDev {
     uint32_t n_alns;
     replay::Params prm;
     uint8_t *slabs;
-    uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_dfa;  // byte offsets inside a slab (header at 0, records at SLAB_CELLS)
+    uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_bits, off_dfa;  // byte offsets inside a slab (header at 0, records at SLAB_CELLS)
     uint32_t max_items;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
     uint32_t *stats;  // per alignment: queued, visited, pruned, item high-water mark
 };
 
-constexpr int REPLAY_MAX_WARPS_PER_CTA = 2;  // 1 warp per CTA spreads few workers over all SMs; 2 reaches 64 warps/SM
+// ONE warp per CTA: 32 CTAs are resident per SM, exactly the 32 workers the 64-register build allows. With a single warp the
+// worker's pointer blocks (replay::Scratch, replay::Graph) sit at fixed shared-memory addresses, so an access to any of the
+// worker's dozen arrays takes one LDS for the base instead of the S2R / LDC / IMAD.WIDE chain the compiler kept
+// re-materialising from the kernel parameters (12 % of all executed instructions in the round-2 capture, profiles/README.md).
+constexpr int REPLAY_MAX_WARPS_PER_CTA = 1;
 
 // Slab header (first 256 bytes of a worker's slab; the visited table starts at SLAB_CELLS). The slab buffer is zeroed by the
 // host when it is (re)allocated or its layout changes, so epoch 0 means "never written".
@@ -49,11 +53,11 @@ template <> struct EpochTraits<uint16_t> { static constexpr uint32_t MAX = 0xFFF
 template <> struct EpochTraits<uint32_t> { static constexpr uint32_t MAX = 0xFFFFFFFEu; };
 
 // Start of one alignment on a worker, all 32 lanes: next epoch (zeroing the table only when the counter wraps), bucket
-// heads of the priorities the previous alignment touched, reached bounds of this graph's nodes, the queue window.
-// Returns the epoch (warp-uniform).
+// heads of the priorities the previous alignment touched, reached bounds and reached-offset bitmap of this graph's nodes,
+// the queue window. Returns the epoch (warp-uniform).
 template <typename CellT>
-__device__ __forceinline__ uint32_t worker_begin_alignment(uint8_t *slab, uint64_t cell_bytes, uint64_t off_qhead, uint64_t off_rb, uint32_t V,
-                                                           uint32_t *s_qwin, uint32_t lane) {
+__device__ __forceinline__ uint32_t worker_begin_alignment(uint8_t *slab, uint64_t cell_bytes, uint64_t off_qhead, uint64_t off_rb, uint64_t off_bits,
+                                                           uint32_t V, uint32_t Wb, uint32_t *s_qwin, uint32_t lane) {
     SlabHeader *hdr = reinterpret_cast<SlabHeader *>(slab);
     uint32_t ep = hdr->epoch + 1, dirty = hdr->dirty_f;
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -68,6 +72,9 @@ __device__ __forceinline__ uint32_t worker_begin_alignment(uint8_t *slab, uint64
     uint4 *p2 = reinterpret_cast<uint4 *>(slab + off_rb);
     const uint32_t n2 = (uint32_t)(((uint64_t)V * 2 + 3) / 4);
     for (uint32_t i = lane; i < n2; i += 32) p2[i] = z;
+    uint4 *p3 = reinterpret_cast<uint4 *>(slab + off_bits);
+    const uint32_t n3 = (uint32_t)(((uint64_t)V * Wb + 3) / 4);
+    for (uint32_t i = lane; i < n3; i += 32) p3[i] = z;
     for (uint32_t i = lane; i < replay::QWIN * 3; i += 32) s_qwin[i] = 0;
     __syncwarp();
     return ep;
@@ -81,11 +88,12 @@ __device__ __forceinline__ void worker_end_alignment(uint8_t *slab, uint32_t epo
 // MINB = minimum resident CTAs per SM the register allocation must allow. Only lane 0 of a warp runs the state machine
 // but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
 template <typename CellT, int MINB, int HEUR>
-__global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_kernel(ReplayDev B) {
-    __shared__ uint32_t s_qwin[REPLAY_MAX_WARPS_PER_CTA][replay::QWIN * 3];  // queue-head window of each worker
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + wib;
-    uint8_t *slab = B.slabs + (uint64_t)worker * B.slab_bytes;
+__global__ void __launch_bounds__(32, MINB) replay_kernel(ReplayDev B) {
+    __shared__ uint32_t s_qwin[replay::QWIN * 3];  // queue-head window of the worker
+    __shared__ replay::Scratch s_scr;              // the worker's pointer blocks at fixed shared-memory addresses
+    __shared__ replay::Graph s_gr;
+    const uint32_t lane = threadIdx.x;
+    uint8_t *slab = B.slabs + (uint64_t)blockIdx.x * B.slab_bytes;
     for (;;) {
         uint32_t a = 0;
         if (lane == 0) a = atomicAdd(B.counter, 1u);
@@ -94,9 +102,10 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
         const AlnDesc ad = B.alns[a];
         const RGraphDesc gd = B.graphs[ad.graph];
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
-        const uint32_t epoch = worker_begin_alignment<CellT>(slab, B.off_qhead - SLAB_CELLS, B.off_qhead, B.off_rb, gd.V, s_qwin[wib], lane);
-        {
-            replay::Graph g;
+        const uint32_t Wb = (dims.W + 31) / 32;
+        const uint32_t epoch = worker_begin_alignment<CellT>(slab, B.off_qhead - SLAB_CELLS, B.off_qhead, B.off_rb, B.off_bits, gd.V, Wb, s_qwin, lane);
+        if (lane == 0) {
+            replay::Graph &g = s_gr;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
             g.nodes = B.nodes + gd.node_base;
             g.succ = B.succ + gd.succ_base;
@@ -104,22 +113,20 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             g.bub = reinterpret_cast<const replay::BubQ *>(B.bub) + gd.bub_base;
             g.path_off = B.path_off + gd.pathoff_base;
             g.path_rem = B.path_rem + gd.path_base;
-            replay::Scratch s;
+            replay::Scratch &s = s_scr;
             s.planes = slab + SLAB_CELLS;
             s.epoch = epoch;
             s.qhead = reinterpret_cast<uint32_t *>(slab + B.off_qhead);
-            s.qwin = s_qwin[wib];
+            s.qwin = s_qwin;
             s.items = reinterpret_cast<replay::Item *>(slab + B.off_items);
             s.free_slots = reinterpret_cast<uint32_t *>(slab + B.off_free);
             s.rb = reinterpret_cast<uint32_t *>(slab + B.off_rb);
+            s.rbits = reinterpret_cast<uint32_t *>(slab + B.off_bits);
+            s.Wb = Wb;
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
             s.W = dims.W, s.f_max = dims.f_max;
             s.max_items = B.max_items;
-#if defined(RP_PROFILE)
-            const long long t_begin = clock64();
-#endif
             replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
-            if (lane == 0) {
             const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             worker_end_alignment(slab, epoch, search.f_top);
             B.scores[a] = r.score;
@@ -127,17 +134,6 @@ __global__ void __launch_bounds__(REPLAY_MAX_WARPS_PER_CTA * 32, MINB) replay_ke
             B.status[a] = r.status;
             B.stats[4 * a + 0] = r.num_queued, B.stats[4 * a + 1] = r.num_visited, B.stats[4 * a + 2] = r.num_pruned;
             B.stats[4 * a + 3] = search.n_items;
-#if defined(RP_PROFILE)
-            {
-                const long long total = clock64() - t_begin;
-                if (a < 8)
-                    printf("aln %u: total %lld cyc, prune %lld (%.1f%%, %u calls, %lld cyc/call), push %lld (%.1f%%), visited %u queued %u pruned %u -> %lld cyc/visit\n",
-                           a, total, search.prof_prune, 100.0 * search.prof_prune / total, search.prof_n_prune,
-                           search.prof_prune / (search.prof_n_prune ? search.prof_n_prune : 1), search.prof_push,
-                           100.0 * search.prof_push / total, r.num_visited, r.num_queued, r.num_pruned, total / (r.num_visited ? r.num_visited : 1));
-            }
-#endif
-            }
         }
         __syncwarp();
     }

@@ -237,7 +237,9 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     }
     std::vector<Item> items(max_items);
     std::vector<uint32_t> free_slots(max_items);
-    Scratch s{planes.data(), epoch, qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), dfa.data(), d.W, max_items, d.f_max};
+    const uint32_t Wb = (d.W + 31) / 32;
+    std::vector<uint32_t> rbits((size_t)view->n_nodes * Wb, 0);
+    Scratch s{planes.data(), epoch, qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), rbits.data(), Wb, dfa.data(), d.W, max_items, d.f_max};
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
