@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(FILL_THREADS) dp_fill_kernel(BatchDev P) {
 
 }  // namespace poasta
 #include "dp_warp_kernel.cuh"
+#include "dp_packed_kernel.cuh"
 namespace poasta {
 
 // gap_affine.rs:804-915 on the trace words. One thread per alignment.
@@ -525,9 +526,26 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     // warp-per-alignment kernel when every query fits 32 lanes x 32 columns, else the CTA-per-alignment kernel
     static const bool force_cta = getenv("POASTA_DP_KERNEL") && !strcmp(getenv("POASTA_DP_KERNEL"), "cta");
     const bool use_warp = pb.max_W <= (uint32_t)WARP_MAX_W && pb.max_in_degree <= 1023 && !force_cta;
-    const size_t per_slot = use_warp ? (size_t)pb.max_store_cells * 2 * sizeof(int) : (size_t)pb.max_cells * 2 * sizeof(int);
+    // packed s16x2 kernel (dp_packed_kernel.cuh) when the optimal score provably stays below its 16-bit "infinite" and the
+    // insertion prefix-min offsets fit: every global alignment costs at most "delete a whole path, insert the whole query"
+    static const bool force_s32 = getenv("POASTA_DP_KERNEL") && !strcmp(getenv("POASTA_DP_KERNEL"), "warp32");
+    const uint64_t worst_opt = 2ull * prm.gap_open + (uint64_t)prm.gap_extend * ((uint64_t)pb.max_V + pb.max_Q) + prm.mismatch;
+    const bool use_packed = use_warp && !force_s32 && pb.acgt_only && worst_opt < PK_INF && (uint64_t)prm.gap_extend * 1024 <= PK_KMAX;
+    const size_t per_slot = use_packed ? std::max<size_t>(16, (size_t)pb.max_n_stored * 32 * 128)
+                            : use_warp ? (size_t)pb.max_store_cells * 2 * sizeof(int) : (size_t)pb.max_cells * 2 * sizeof(int);
     size_t slots = (size_t)c.n_sms * 4;  // CTA slots of the CTA-per-alignment kernel
-    if (use_warp) {                      // warp slots: what the register file lets be resident
+    if (use_packed) {
+        static bool attr_set[16] = {};
+        if (!attr_set[c.device & 15]) {
+            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
+            attr_set[c.device & 15] = true;
+        }
+        int ctas = 0;
+        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<false>, PK_WARPS * 32, PK_SMEM_BYTES);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<true>, PK_WARPS * 32, PK_SMEM_BYTES);
+        slots = (size_t)c.n_sms * std::max(1, ctas) * PK_WARPS;
+    } else if (use_warp) {               // warp slots: what the register file lets be resident
         int ctas = 0;
         if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<false>, WARP_KERNEL_WARPS * 32, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_warp_kernel<true>, WARP_KERNEL_WARPS * 32, 0);
@@ -536,7 +554,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     slots = std::min<size_t>(slots, use_warp ? ((size_t)n + 3) / 4 * 4 : n);
     const size_t scratch_budget = std::max<size_t>(((size_t)8 << 30) / tl_lane_count, c.scratch.cap);
     while (slots > 4 && slots * per_slot > scratch_budget) slots = std::max<size_t>(4, slots / 2 / 4 * 4);
-    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(use_warp ? (scores_only ? 16 : pb.ptrace_words * 4) : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
+    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(use_packed ? (scores_only ? 16 : pb.prow_halves * 2) : use_warp ? (scores_only ? 16 : pb.ptrace_words * 4) : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
               c.node_id.reserve(pb.node_id.size() * 4) && c.ord_slot.reserve(pb.ord_slot.size() * 4) &&
@@ -595,7 +613,11 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.status = (int32_t *)c.status.d;
 
     CK(cudaEventRecord(c.ev0, s));
-    if (use_warp) {
+    if (use_packed) {
+        const unsigned grid = (unsigned)(slots / PK_WARPS), block = PK_WARPS * 32;
+        if (scores_only) dp_fill_packed_kernel<false><<<grid, block, PK_SMEM_BYTES, s>>>(P);
+        else dp_fill_packed_kernel<true><<<grid, block, PK_SMEM_BYTES, s>>>(P);
+    } else if (use_warp) {
         const unsigned grid = (unsigned)(slots / WARP_KERNEL_WARPS), block = WARP_KERNEL_WARPS * 32;
         if (scores_only) dp_fill_warp_kernel<false><<<grid, block, 0, s>>>(P);
         else dp_fill_warp_kernel<true><<<grid, block, 0, s>>>(P);
@@ -625,7 +647,8 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         return 0;
     }
     const unsigned tb_blocks = (n + 127) / 128;
-    if (use_warp) traceback_planes_kernel<<<tb_blocks, 128, 0, s>>>(P);
+    if (use_packed) traceback_rows_kernel<<<tb_blocks, 128, 0, s>>>(P);
+    else if (use_warp) traceback_planes_kernel<<<tb_blocks, 128, 0, s>>>(P);
     else if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
     else traceback_kernel<uint16_t><<<tb_blocks, 128, 0, s>>>(P);
     scan_kernel<<<1, 1024, 0, s>>>(P.n_pairs, (uint32_t *)c.offsets.d, n);
@@ -723,7 +746,7 @@ static int dp_problems(int device, const std::vector<Problem> &probs, const poas
                 for (uint32_t v = 0; v < p.graph->n_nodes; ++v) merge_rows += p.graph->pred_off[v + 1] - p.graph->pred_off[v] >= 2;
                 budget_key = p.graph_key, have_budget_key = true;
             }
-            const uint64_t add = std::max<uint64_t>(V * ((p.qlen + 4) & ~3ull) * 4, V * 1024 + merge_rows * 4096);
+            const uint64_t add = std::max<uint64_t>(V * ((p.qlen + 1 + 31) & ~31ull) * 4, V * 1024 + merge_rows * 4096);  // packed rows: 4 B per cell, 32-column lanes
             if (!pb.alns.empty() && (chunk_bytes + add > budget || pb.alns.size() >= (1u << 20))) break;
             chunk_bytes += add;
             if (p.graph_key != last_key || pb.graphs.empty()) {

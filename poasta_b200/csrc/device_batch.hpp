@@ -40,6 +40,7 @@ struct AlnDesc {
     uint64_t ptrace_base; // into the trace store (32-bit words): V * 256 bit-plane words + n_ord_rows * 1024 ordinals (warp kernel)
     uint32_t out_base;    // into the pair output staging area, capacity V + Q + 2
     uint32_t out_cap;
+    uint64_t prow_base;   // into the trace store (16-bit halves): V rows of ceil(W / 32) * 64 halves, M then D (packed kernel)
 };
 
 constexpr uint32_t INFO_ALWAYS_OPEN = 1u << 8;
@@ -63,6 +64,7 @@ constexpr uint32_t ROW_PREV_IN_REGS = 0xFFFFFFFFu;
 // One graph in the kernels' rank-ordered layout (see the header comment); pred_off is relative to this graph's pred_rank.
 struct PackedGraph {
     uint32_t V = 0, max_in_degree = 0, n_stored = 0, n_ord_rows = 0;
+    bool acgt_only = true;  // every real node carries A, C, G or T (the packed kernel's symbol tables)
     std::vector<uint8_t> node_sym;
     std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
     std::vector<RowRec> rows;
@@ -75,9 +77,14 @@ struct PackedGraph {
         node_sym.reserve(V), node_info.reserve(V), node_id.reserve(V), ord_slot.reserve(V), pred_off.reserve(V + 1);
         pred_rank.reserve(g.pred_off[V]);
         max_in_degree = n_stored = n_ord_rows = 0;
+        acgt_only = true;
         for (uint32_t r = 0; r < V; ++r) {
             const uint32_t v = g.topo_order[r];
             node_sym.push_back(g.symbol[v]);
+            if (v != g.start_node && v != g.end_node) {
+                const uint8_t c = g.symbol[v];
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') acgt_only = false;
+            }
             node_id.push_back(v);
             ord_slot.push_back(g.pred_off[v + 1] - g.pred_off[v] >= 2 ? n_ord_rows++ : 0xFFFFFFFFu);
             uint32_t info = 0;
@@ -138,6 +145,10 @@ struct PackedBatch {
     std::vector<uint8_t> queries;
     uint64_t trace_elems = 0;
     uint64_t ptrace_words = 0;
+    uint64_t prow_halves = 0;  // packed kernel's M / D row store
+    uint32_t max_n_stored = 0; // max over alignments of the graph's n_stored
+    uint32_t max_V = 0, max_Q = 0;
+    bool acgt_only = true;
     uint64_t out_elems = 0;
     uint64_t max_cells = 0;  // max over alignments of V * W
     uint64_t max_store_cells = 0;  // max over alignments of n_stored * W (warp kernel's compact row store)
@@ -157,8 +168,9 @@ struct PackedBatch {
         pred_slot.clear();
         rows.clear();
         queries.clear();
-        trace_elems = ptrace_words = out_elems = max_cells = total_cells = max_store_cells = 0;
-        max_in_degree = 0;
+        trace_elems = ptrace_words = prow_halves = out_elems = max_cells = total_cells = max_store_cells = 0;
+        max_in_degree = max_n_stored = max_V = max_Q = 0;
+        acgt_only = true;
         max_W = 0;
     }
 
@@ -191,6 +203,7 @@ struct PackedBatch {
         pred_rank.insert(pred_rank.end(), pg.pred_rank.begin(), pg.pred_rank.end());
         pred_slot.insert(pred_slot.end(), pg.pred_slot.begin(), pg.pred_slot.end());
         max_in_degree = std::max(max_in_degree, gd.max_in_degree);
+        acgt_only = acgt_only && pg.acgt_only;
         graphs.push_back(gd);
         return (uint32_t)graphs.size() - 1;
     }
@@ -208,6 +221,10 @@ struct PackedBatch {
         trace_elems += V * a.W;
         a.ptrace_base = ptrace_words;
         ptrace_words += V * 256 + (uint64_t)graphs[graph].n_ord_rows * 1024;
+        a.prow_base = prow_halves;
+        prow_halves += V * (uint64_t)((a.W + 31) / 32) * 64;
+        max_n_stored = std::max(max_n_stored, graphs[graph].n_stored);
+        max_V = std::max<uint32_t>(max_V, (uint32_t)V), max_Q = std::max(max_Q, Q);
         a.out_cap = (uint32_t)V + Q + 2;
         a.out_base = (uint32_t)out_elems;
         out_elems += a.out_cap;

@@ -1,0 +1,352 @@
+// dp_fill_packed_kernel — the M/I/D fill with two 16-bit scores per register (included by align.cu after dp_warp_kernel.cuh).
+//
+// Same mapping as dp_fill_warp_kernel (one WARP per alignment, lane l owns the 32 query columns [32 l, 32 l + 32) of every
+// row, no block barriers), but a lane's 32 columns live in 16 registers of packed s16x2 scores and every recurrence is a
+// Blackwell DPX / packed instruction that updates two cells at once:
+//   diagonal term       PRMT (shift the previous row by one column) + IADD (packed mismatch cost from a per-symbol table)
+//   deletion            IADD, LOP3 (packed select: a deletion opens only where the next query base differs from the node
+//                       symbol, dfa.rs:210-250) and VIMNMX3.S16x2  = __vimin3_s16x2(open, extend, INF)
+//   min(diagonal, D)    VIMNMX.S16x2    = __vmins2
+//   insertion chain     I[j] = o + min_{k<j, openI(k)} (X[k] + (j - k) e): per pair IADD, LOP3, two VIMNMX.S16x2 and one PRMT for the
+//                       running prefix-min inside the lane, ONE 5-step warp-shuffle prefix-min per row across lanes
+//   final M             VIMNMX3.S16x2   = __vimin3_s16x2(X, I, INF)
+// = 20 instructions per PAIR of cells (the s32 kernel needs ~27 per cell when it also derives the traceback bits).
+//
+// Traceback: the kernel writes NO per-cell decision bits. It stores the M and D rows themselves (2 x u16 per cell, fully
+// coalesced 16-byte chunks: chunk t of lane l sits at (t * lanes + l) * 16 bytes of the row), and traceback_rows_kernel applies the
+// reference's score-equality backtrace (gap_affine.rs:550-657, 804-915) to those tables directly — the literal rule set, so
+// predecessor ordinals, "first predecessor in order wins" and the equality quirks need no encoding. The same rows are the
+// row store that rows with several predecessors (or a predecessor that is not the row just before) read back. I is never
+// stored: M == I is implied when neither a diagonal predecessor nor D equals M, and an insertion state always steps to
+// (node, offset - 1, Match) (gap_affine.rs:639-650).
+//
+// Arithmetic: "infinite" is any value >= PK_INF = 0x5000; M and D are clamped to PK_INF in the same VIMNMX3 that forms them,
+// so no half ever reaches 0x8000 and plain 32-bit adds never carry between the halves. Clamping is exact for every cell
+// whose true value is below PK_INF (its optimal predecessors are smaller still), and the host picks this kernel only when the
+// optimal score is provably below PK_INF: 2 o + e (V + Q) + x < PK_INF, e * 1024 <= PK_KMAX (align.cu: run_chunk).
+#pragma once
+
+namespace poasta {
+
+constexpr uint32_t PK_INF = 0x5000u, PK_INF2 = 0x50005000u;   // infinite score (per half)
+constexpr uint32_t PK_BIG = 0x7E00u, PK_BIG2 = 0x7E007E00u;   // "no candidate" of the insertion prefix-min (>= any candidate)
+constexpr uint32_t PK_KMAX = 11000u;                          // largest (lanes * 32) * e the prefix-min offsets may reach
+constexpr int PK_WARPS = 4;
+constexpr int PK_TAB_WORDS = 2 * 4 * 16 * 32;                 // per warp: E and N tables, 4 symbols, 16 pairs, 32 lanes (16 KB)
+constexpr size_t PK_SMEM_BYTES = (size_t)PK_WARPS * PK_TAB_WORDS * 4;
+
+// node symbols index the per-symbol tables; the host picks this kernel only for graphs over A, C, G, T (start / end rows carry no
+// symbol: their diagonal and deletion terms are infinite or symbol-free, so any table serves)
+__device__ __forceinline__ int pk_sym_index(int s) { return s == 'C' ? 1 : (s == 'G' ? 2 : (s == 'T' ? 3 : 0)); }
+
+// Row r of an alignment's store: lanes * 64 halves = [M: 4 chunks x lanes x 8 halves][D: the same]; as uint4: 8 * lanes per row.
+template <bool WRITE_ROWS>
+__global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchDev P) {
+    extern __shared__ uint4 pk_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t worker = blockIdx.x * PK_WARPS + wib;
+    uint4 *const tabE = pk_smem + (size_t)wib * (PK_TAB_WORDS / 4);  // [sym][chunk][lane] uint4 (4 pairs per chunk)
+    uint4 *const tabN = tabE + 4 * 4 * 32;
+    uint4 *const slot = reinterpret_cast<uint4 *>(P.scratch + (uint64_t)worker * P.scratch_stride);  // scores-only: compact row store
+    const uint32_t x2 = (uint32_t)P.x * 0x10001u, oe2 = (uint32_t)P.oe * 0x10001u, e2 = (uint32_t)P.e * 0x10001u;
+    const uint32_t o2 = (uint32_t)(P.oe - P.e) * 0x10001u;
+    const int j0 = lane * 32;
+
+    for (;;) {
+        uint32_t a = 0;
+        if (lane == 0) a = atomicAdd(P.counter, 1u);
+        a = __shfl_sync(0xFFFFFFFFu, a, 0);
+        if (a >= P.n_alns) break;
+        const AlnDesc ad = P.alns[a];
+        const GraphDesc gd = P.graphs[ad.graph];
+        const int Q = (int)ad.Q, V = (int)gd.V;
+        const int nl = ((int)ad.W + 31) >> 5;  // lanes that own columns
+        const bool lane_active = lane < nl;
+        const uint8_t *q = P.queries + ad.query_base;
+        const RowRec *rows = P.rows + gd.node_base;
+        const uint32_t *prank = P.pred_rank + gd.pred_base, *pslot = P.pred_slot + gd.pred_base;
+        uint4 *const store = WRITE_ROWS ? reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(P.trace) + ad.prow_base) : slot;
+        const int row_u4 = 8 * nl;
+
+        // per-symbol tables of this lane's columns
+        __syncwarp();
+        // Packed per-symbol tables of this lane's columns (pair k = columns j0 + 2k, j0 + 2k + 1; 0xFFFF per half where it holds):
+        //   E  column j matches s:            1 <= j <= Q && q[j - 1] == s
+        //   N  the next query base equals s:  j < Q && q[j] == s
+        {
+            uint32_t *wE = reinterpret_cast<uint32_t *>(tabE), *wN = reinterpret_cast<uint32_t *>(tabN);
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) {
+                const int j = j0 + 2 * k;
+                const int qm = (j >= 1 && j <= Q) ? q[j - 1] : 256, q0 = j < Q ? q[j] : 256, q1 = j + 1 < Q ? q[j + 1] : 256;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int sym = s == 0 ? 'A' : (s == 1 ? 'C' : (s == 2 ? 'G' : 'T'));
+                    const uint32_t E = (qm == sym ? 0xFFFFu : 0u) | (q0 == sym ? 0xFFFF0000u : 0u);  // column j + 1 <= Q matches q[j]
+                    const uint32_t N = (q0 == sym ? 0xFFFFu : 0u) | (q1 == sym ? 0xFFFF0000u : 0u);
+                    const int w = ((s * 4 + (k >> 2)) * 32 + lane) * 4 + (k & 3);
+                    wE[w] = E, wN[w] = N;
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t K[16];  // (Wc - j) e per half, Wc = 32 nl: the offsets of the insertion prefix-min (always >= e)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t lo = (uint32_t)(32 * nl - (j0 + 2 * k)) * (uint32_t)P.e, hi = lo - (uint32_t)P.e;
+            K[k] = lane_active ? (lo | (hi << 16)) : 0u;
+        }
+
+        uint32_t Pm[16], Pd[16];  // the previous row (rank r - 1), then the gathered predecessor row, then this row's M and D
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Pm[k] = Pd[k] = PK_INF2;
+
+        RowRec next_row = rows[0];
+        for (int r = 0; r < V; ++r) {
+            const RowRec row = next_row;
+            if (r + 1 < V) next_row = rows[r + 1];  // in flight while this row is computed
+            const uint32_t inf = row.info;
+            const int vs = (int)(row.npred_sym >> 24);
+            const bool is_end = inf & INFO_IS_END, is_start = inf & INFO_IS_START;
+            const int npred = (int)(row.npred_sym & 0xFFFFFFu);
+
+            // ---- gather: elementwise minimum of the predecessor rows (min commutes with the column shift and the costs) ----
+            if (!(npred == 1 && row.pred0_slot == ROW_PREV_IN_REGS)) {
+                uint32_t Am[16], Ad[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) Am[k] = Ad[k] = PK_INF2;
+                const uint32_t pb = row.pred_begin, pe = pb + (uint32_t)npred;
+                for (uint32_t kk = pb; kk < pe; ++kk) {
+                    const uint32_t pr = prank[kk];
+                    if (!WRITE_ROWS && (int)pr == r - 1) {  // scores-only: the row just computed may have no slot in the compact store
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) Am[k] = __vmins2(Am[k], Pm[k]), Ad[k] = __vmins2(Ad[k], Pd[k]);
+                    } else if (lane_active) {
+                        const uint4 *src = store + (uint64_t)(WRITE_ROWS ? pr : pslot[kk]) * row_u4 + lane;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const uint4 m = src[t * nl], d = src[(4 + t) * nl];
+                            Am[4 * t] = __vmins2(Am[4 * t], m.x), Am[4 * t + 1] = __vmins2(Am[4 * t + 1], m.y);
+                            Am[4 * t + 2] = __vmins2(Am[4 * t + 2], m.z), Am[4 * t + 3] = __vmins2(Am[4 * t + 3], m.w);
+                            Ad[4 * t] = __vmins2(Ad[4 * t], d.x), Ad[4 * t + 1] = __vmins2(Ad[4 * t + 1], d.y);
+                            Ad[4 * t + 2] = __vmins2(Ad[4 * t + 2], d.z), Ad[4 * t + 3] = __vmins2(Ad[4 * t + 3], d.w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) Pm[k] = Am[k], Pd[k] = Ad[k];
+            }
+
+            // ---- diagonal, deletion, X = min(diagonal, D) ----
+            uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Pm[15], 1);  // its high half is column j0 - 1
+            if (lane == 0) left = PK_INF2;
+            uint32_t X[16];
+            const int si = pk_sym_index(vs);
+            if (is_end) {
+                // M(end, j) = min over predecessors of M(p, j): same column, no symbol; no deletion is opened into `end`
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t d = __vimin3_s16x2(Pd[k] + e2, PK_INF2, PK_INF2);
+                    X[k] = __vmins2(Pm[k], d);
+                    Pd[k] = d;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint4 e4 = tabE[(si * 4 + t) * 32 + lane], n4 = tabN[(si * 4 + t) * 32 + lane];
+                    const uint32_t E[4] = {e4.x, e4.y, e4.z, e4.w}, N[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int k = 4 * t + p;
+                        const uint32_t prev = k == 0 ? left : Pm[k - 1];
+                        const uint32_t diag = __byte_perm(prev, Pm[k], 0x5432);           // (M[j - 1], M[j]) of the predecessor row
+                        const uint32_t mdiag = diag + (~E[p] & x2);                         // + mismatch cost where q[j - 1] != symbol
+                        const uint32_t dopen = ((Pm[k] + oe2) & ~N[p]) | (PK_INF2 & N[p]);  // open only where q[j] != symbol
+                        const uint32_t d = __vimin3_s16x2(dopen, Pd[k] + e2, PK_INF2);
+                        X[k] = __vmins2(mdiag, d);
+                        Pd[k] = d;
+                    }
+                }
+            }
+            if (is_start && lane == 0) X[0] &= 0xFFFF0000u;  // M(start, 0) = 0
+
+            // ---- insertion chain: prefix-min over the whole row ----
+            // an insertion opens at column k only if the node has a successor that is `end` or mismatches q[k]
+            const bool any_open = (inf & INFO_HAS_SUCC) && !is_end;
+            const bool always_open = inf & INFO_ALWAYS_OPEN;
+            const int ui = pk_sym_index((int)(inf & 0xFF));
+            uint32_t FI[16];  // 0xFFFF per half where no insertion may open
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint4 n4 = make_uint4(0u, 0u, 0u, 0u);
+                if (!any_open) {
+                    n4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+                } else if (!always_open) {
+                    n4 = tabN[(ui * 4 + t) * 32 + lane];
+                }
+                FI[4 * t] = n4.x, FI[4 * t + 1] = n4.y, FI[4 * t + 2] = n4.z, FI[4 * t + 3] = n4.w;
+            }
+            uint32_t rm = PK_BIG2;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t av = ((X[k] + K[k]) & ~FI[k]) | (PK_BIG2 & FI[k]);
+                rm = __vmins2(rm, av);
+            }
+            int run = (int)min(rm & 0xFFFFu, rm >> 16);
+            if (!lane_active) run = (int)PK_BIG;
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl = min(incl, o);
+            }
+            int pm = __shfl_up_sync(0xFFFFFFFFu, incl, 1);  // exclusive prefix-min over all columns left of mine
+            if (lane == 0) pm = (int)PK_BIG;
+            uint32_t pmv = (uint32_t)pm * 0x10001u;
+
+            // ---- final M ----
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t av = ((X[k] + K[k]) & ~FI[k]) | (PK_BIG2 & FI[k]);
+                const uint32_t pre = __vmins2(pmv, __byte_perm(av, PK_BIG2, 0x1054));  // (pm, min(pm, av.lo)): exclusive per column
+                const uint32_t iv = (pre - K[k]) + o2;                                  // I[j] = pre + o - (Wc - j) e
+                Pm[k] = __vimin3_s16x2(X[k], iv, PK_INF2);
+                const uint32_t t2 = __vmins2(pre, av);
+                pmv = __byte_perm(t2, t2, 0x3232);                                      // min(pm, av.lo, av.hi) in both halves
+            }
+
+            // ---- store the row ----
+            if (lane_active && (WRITE_ROWS || (inf & INFO_STORE))) {
+                uint4 *dst = store + (uint64_t)(WRITE_ROWS ? (uint32_t)r : (inf >> INFO_SLOT_SHIFT)) * row_u4 + lane;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    dst[t * nl] = make_uint4(Pm[4 * t], Pm[4 * t + 1], Pm[4 * t + 2], Pm[4 * t + 3]);
+                    dst[(4 + t) * nl] = make_uint4(Pd[4 * t], Pd[4 * t + 1], Pd[4 * t + 2], Pd[4 * t + 3]);
+                }
+            }
+            if (is_end && j0 <= Q && Q < j0 + 32) {
+                uint32_t sc = PK_INF;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (j0 + 2 * k == Q) sc = Pm[k] & 0xFFFFu;
+                    if (j0 + 2 * k + 1 == Q) sc = Pm[k] >> 16;
+                }
+                P.scores[a] = sc < PK_INF ? sc : (uint32_t)INF;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// gap_affine.rs:550-657 + 804-915 on the M / D rows written by dp_fill_packed_kernel<true>. One thread per alignment.
+__global__ void traceback_rows_kernel(BatchDev P) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.n_alns) return;
+    const AlnDesc ad = P.alns[a];
+    const GraphDesc gd = P.graphs[ad.graph];
+    const int Q = (int)ad.Q, V = (int)gd.V;
+    const int nl = ((int)ad.W + 31) >> 5;
+    const uint32_t *node_id = P.node_id + gd.node_base;
+    const uint8_t *sym = P.node_sym + gd.node_base;
+    const uint32_t *poff = P.pred_off + gd.predoff_base;
+    const uint8_t *q = P.queries + ad.query_base;
+    const uint16_t *rows = reinterpret_cast<const uint16_t *>(P.trace) + ad.prow_base;
+    const int x = P.x, oe = P.oe, e = P.e;
+    uint32_t *out_r = P.out_r + ad.out_base, *out_q = P.out_q + ad.out_base;
+    uint32_t pos = ad.out_cap;  // fill from the back
+    int32_t status = 0;
+    const uint32_t score = P.scores[a];
+    // score of (rank r, column j); plane 0 = M, 1 = D; -1 = unvisited
+    auto val = [&](int r, int j, int plane) -> int {
+        const int l = j >> 5, c = j & 31;
+        const uint32_t v = rows[(uint64_t)r * (nl * 64) + (uint32_t)plane * (nl * 32) + (uint32_t)(((c >> 3) * nl + l) * 8 + (c & 7))];
+        return v >= PK_INF ? -1 : (int)v;
+    };
+    if (score >= (uint32_t)INF) {
+        status = POASTA_ERR_NO_ALIGNMENT;
+    } else if (Q == 1) {  // gap_affine.rs:812-824
+        --pos;
+        out_r[pos] = node_id[V - 1];
+        out_q[pos] = 0;
+    } else if (Q > 1) {
+        auto step = [&](int r, int o, int s, int &nr, int &no, int &ns) -> bool {
+            const uint32_t pb = poff[r], pe = poff[r + 1];
+            if (s == 0) {
+                const int cur = val(r, o, 0);
+                if (cur < 0) return false;
+                if (o > 0) {  // predecessors first, in the reference's Incoming order
+                    const bool end_row = r == V - 1;
+                    const bool me = end_row || sym[r] == q[o - 1];
+                    const int po = end_row ? o : o - 1, want = me ? cur : cur - x;
+                    if (want >= 0)
+                        for (uint32_t k = pb; k < pe; ++k) {
+                            const int p = (int)P.pred_rank[k];
+                            if (val(p, po, 0) == want) {
+                                nr = p, no = po, ns = 0;
+                                return true;
+                            }
+                        }
+                }
+                if (val(r, o, 1) == cur) {
+                    nr = r, no = o, ns = 1;
+                    return true;
+                }
+                // M is the minimum of the diagonal candidates, D and I: neither of the first two equals it, so I does
+                if (o > 0 && r != V - 1) {
+                    nr = r, no = o, ns = 2;
+                    return true;
+                }
+                return false;
+            } else if (s == 1) {
+                const int cur = val(r, o, 1);
+                if (cur < 0) return false;
+                const int w1 = cur - oe, w2 = cur - e;
+                if (w1 >= 0)
+                    for (uint32_t k = pb; k < pe; ++k) {
+                        const int p = (int)P.pred_rank[k];
+                        if (val(p, o, 0) == w1) {
+                            nr = p, no = o, ns = 0;
+                            return true;
+                        }
+                    }
+                if (w2 >= 0)
+                    for (uint32_t k = pb; k < pe; ++k) {
+                        const int p = (int)P.pred_rank[k];
+                        if (val(p, o, 1) == w2) {
+                            nr = p, no = o, ns = 1;
+                            return true;
+                        }
+                    }
+                return false;
+            } else {
+                if (o <= 0) return false;
+                nr = r, no = o - 1, ns = 0;  // open and extend both resume in Match state (gap_affine.rs:639-650)
+                return true;
+            }
+        };
+        int cr = V - 1, co = Q, cs = 0, br = 0, bo = 0, bs = 0;
+        if (step(cr, co, cs, br, bo, bs)) {
+            cr = br, co = bo, cs = bs;
+            while (step(cr, co, cs, br, bo, bs)) {
+                if (cs == 0 && bs != 0) {
+                    cr = br, co = bo, cs = bs;
+                    continue;
+                }
+                if (pos == 0) {
+                    status = POASTA_ERR_UNSUPPORTED;
+                    break;
+                }
+                --pos;
+                if (cs == 0) out_r[pos] = node_id[cr], out_q[pos] = (uint32_t)(co - 1);
+                else if (cs == 2) out_r[pos] = POASTA_NONE, out_q[pos] = (uint32_t)(co - 1);
+                else out_r[pos] = node_id[cr], out_q[pos] = POASTA_NONE;
+                if (br == 0) break;  // predecessor is the start node (rank 0)
+                cr = br, co = bo, cs = bs;
+            }
+        }
+    }
+    P.n_pairs[a] = ad.out_cap - pos;
+    P.status[a] = status;
+}
+
+}  // namespace poasta

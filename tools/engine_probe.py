@@ -13,7 +13,8 @@ seqs = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 length = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 rate = float(sys.argv[5]) if len(sys.argv) > 5 else 0.05
 fastas = [synth.config2_family(f, n_seqs=seqs, root_len=length, rate=rate) for f in range(F)]
-for rep in range(2):
+import os
+for rep in range(int(os.environ.get('PROBE_REPS', '2'))):
     t0 = time.perf_counter()
     graphs, scores, cells = msa_batch(fastas, device=0)
     wall = time.perf_counter() - t0
