@@ -647,7 +647,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         return 0;
     }
     const unsigned tb_blocks = (n + 127) / 128;
-    if (use_packed) traceback_rows_kernel<<<tb_blocks, 128, 0, s>>>(P);
+    if (use_packed) traceback_rows_kernel<<<(n + 3) / 4, 128, 0, s>>>(P);  // one warp per alignment
     else if (use_warp) traceback_planes_kernel<<<tb_blocks, 128, 0, s>>>(P);
     else if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
     else traceback_kernel<uint16_t><<<tb_blocks, 128, 0, s>>>(P);

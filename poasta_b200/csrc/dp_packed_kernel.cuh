@@ -33,7 +33,34 @@ constexpr uint32_t PK_BIG = 0x7E00u, PK_BIG2 = 0x7E007E00u;   // "no candidate" 
 constexpr uint32_t PK_KMAX = 11000u;                          // largest (lanes * 32) * e the prefix-min offsets may reach
 constexpr int PK_WARPS = 4;
 constexpr int PK_TAB_WORDS = 2 * 4 * 16 * 32;                 // per warp: E and N tables, 4 symbols, 16 pairs, 32 lanes (16 KB)
-constexpr size_t PK_SMEM_BYTES = (size_t)PK_WARPS * PK_TAB_WORDS * 4;
+constexpr int PK_TILE_ROWS = 64;                              // row records per TMA tile (1 KB), two tiles in flight per warp
+constexpr int PK_WARP_SMEM = PK_TAB_WORDS * 4 + 2 * PK_TILE_ROWS * 16 + 16;  // tables + two record tiles + two mbarriers
+constexpr size_t PK_SMEM_BYTES = (size_t)PK_WARPS * PK_WARP_SMEM;
+
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) of a tile of row records ----
+__device__ __forceinline__ uint32_t pk_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pk_mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pk_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void pk_tile_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    // order this warp's earlier (generic-proxy) reads of the buffer before the async-proxy write that reuses it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pk_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pk_smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(pk_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void pk_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra PK_WAIT;\n"
+        "}\n" ::"r"(pk_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // node symbols index the per-symbol tables; the host picks this kernel only for graphs over A, C, G, T (start / end rows carry no
 // symbol: their diagonal and deletion terms are infinite or symbol-free, so any table serves)
@@ -47,6 +74,17 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
     const uint32_t worker = blockIdx.x * PK_WARPS + wib;
     uint4 *const tabE = pk_smem + (size_t)wib * (PK_TAB_WORDS / 4);  // [sym][chunk][lane] uint4 (4 pairs per chunk)
     uint4 *const tabN = tabE + 4 * 4 * 32;
+    // the graph's row records (16 B per row: flags, predecessor summary, symbol) are staged through shared memory in tiles of
+    // PK_TILE_ROWS rows by TMA bulk copies, two tiles ahead of the row being computed; lane 0 issues, an mbarrier per buffer signals
+    RowRec *const tile = reinterpret_cast<RowRec *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)PK_WARPS * PK_TAB_WORDS * 4) + (size_t)wib * 2 * PK_TILE_ROWS;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)PK_WARPS * (PK_TAB_WORDS * 4 + 2 * PK_TILE_ROWS * 16)) + wib * 2;
+    if (lane == 0) {
+        pk_mbar_init(&bars[0]);
+        pk_mbar_init(&bars[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase0 = 0, phase1 = 0;  // parity the next completion of each buffer's mbarrier will have
     uint4 *const slot = reinterpret_cast<uint4 *>(P.scratch + (uint64_t)worker * P.scratch_stride);  // scores-only: compact row store
     const uint32_t x2 = (uint32_t)P.x * 0x10001u, oe2 = (uint32_t)P.oe * 0x10001u, e2 = (uint32_t)P.e * 0x10001u;
     const uint32_t o2 = (uint32_t)(P.oe - P.e) * 0x10001u;
@@ -101,10 +139,26 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
 #pragma unroll
         for (int k = 0; k < 16; ++k) Pm[k] = Pd[k] = PK_INF2;
 
-        RowRec next_row = rows[0];
+        const int n_tiles = (V + PK_TILE_ROWS - 1) / PK_TILE_ROWS;
+        auto issue_tile = [&](int t) {  // lane 0 only
+            const int first = t * PK_TILE_ROWS, cnt = min(PK_TILE_ROWS, V - first);
+            pk_tile_load(tile + (t & 1) * PK_TILE_ROWS, rows + first, (uint32_t)cnt * 16u, &bars[t & 1]);
+        };
+        if (lane == 0) {
+            issue_tile(0);
+            if (n_tiles > 1) issue_tile(1);
+        }
         for (int r = 0; r < V; ++r) {
-            const RowRec row = next_row;
-            if (r + 1 < V) next_row = rows[r + 1];  // in flight while this row is computed
+            if ((r & (PK_TILE_ROWS - 1)) == 0) {  // entering a tile: wait for its copy, refill the buffer the previous tile left
+                const int t = r / PK_TILE_ROWS;
+                if (t >= 1) {
+                    __syncwarp();  // every lane is done with tile t - 1
+                    if (lane == 0 && t + 1 < n_tiles) issue_tile(t + 1);
+                }
+                if (t & 1) pk_mbar_wait(&bars[1], phase1), phase1 ^= 1;
+                else pk_mbar_wait(&bars[0], phase0), phase0 ^= 1;
+            }
+            const RowRec row = tile[((r / PK_TILE_ROWS) & 1) * PK_TILE_ROWS + (r & (PK_TILE_ROWS - 1))];
             const uint32_t inf = row.info;
             const int vs = (int)(row.npred_sym >> 24);
             const bool is_end = inf & INFO_IS_END, is_start = inf & INFO_IS_START;
@@ -238,9 +292,15 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
     }
 }
 
-// gap_affine.rs:550-657 + 804-915 on the M / D rows written by dp_fill_packed_kernel<true>. One thread per alignment.
+// gap_affine.rs:550-657 + 804-915 on the M / D rows written by dp_fill_packed_kernel<true>. One WARP per alignment.
+// Most of a walk is a run of diagonal steps along a chain of rows whose only predecessor is the row before (a match or a
+// mismatch: M(r - 1, o - 1) == M(r, o) [- x]). Lane i tests step i of such a run from the current cell — its loads depend on
+// (r - i, o - i) only — and one ballot gives the length of the run (up to 32 steps per round trip to memory, pairs written
+// coalesced). Where the run stops (a gap, a row with several predecessors, the start or end row) lane 0 takes ONE step with the
+// reference's full rule set and the lanes try again from there.
 __global__ void traceback_rows_kernel(BatchDev P) {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (a >= P.n_alns) return;
     const AlnDesc ad = P.alns[a];
     const GraphDesc gd = P.graphs[ad.graph];
@@ -248,6 +308,7 @@ __global__ void traceback_rows_kernel(BatchDev P) {
     const int nl = ((int)ad.W + 31) >> 5;
     const uint32_t *node_id = P.node_id + gd.node_base;
     const uint8_t *sym = P.node_sym + gd.node_base;
+    const RowRec *recs = P.rows + gd.node_base;
     const uint32_t *poff = P.pred_off + gd.predoff_base;
     const uint8_t *q = P.queries + ad.query_base;
     const uint16_t *rows = reinterpret_cast<const uint16_t *>(P.trace) + ad.prow_base;
@@ -259,15 +320,14 @@ __global__ void traceback_rows_kernel(BatchDev P) {
     // score of (rank r, column j); plane 0 = M, 1 = D; -1 = unvisited
     auto val = [&](int r, int j, int plane) -> int {
         const int l = j >> 5, c = j & 31;
-        const uint32_t v = rows[(uint64_t)r * (nl * 64) + (uint32_t)plane * (nl * 32) + (uint32_t)(((c >> 3) * nl + l) * 8 + (c & 7))];
+        const uint32_t v = __ldg(&rows[(uint64_t)r * (nl * 64) + (uint32_t)plane * (nl * 32) + (uint32_t)(((c >> 3) * nl + l) * 8 + (c & 7))]);
         return v >= PK_INF ? -1 : (int)v;
     };
     if (score >= (uint32_t)INF) {
         status = POASTA_ERR_NO_ALIGNMENT;
     } else if (Q == 1) {  // gap_affine.rs:812-824
         --pos;
-        out_r[pos] = node_id[V - 1];
-        out_q[pos] = 0;
+        if (lane == 0) out_r[pos] = node_id[V - 1], out_q[pos] = 0;
     } else if (Q > 1) {
         auto step = [&](int r, int o, int s, int &nr, int &no, int &ns) -> bool {
             const uint32_t pb = poff[r], pe = poff[r + 1];
@@ -325,28 +385,69 @@ __global__ void traceback_rows_kernel(BatchDev P) {
             }
         };
         int cr = V - 1, co = Q, cs = 0, br = 0, bo = 0, bs = 0;
-        if (step(cr, co, cs, br, bo, bs)) {
-            cr = br, co = bo, cs = bs;
-            while (step(cr, co, cs, br, bo, bs)) {
-                if (cs == 0 && bs != 0) {
-                    cr = br, co = bo, cs = bs;
+        int going = 0;
+        if (lane == 0 && step(cr, co, cs, br, bo, bs)) cr = br, co = bo, cs = bs, going = 1;
+        going = __shfl_sync(0xFFFFFFFFu, going, 0);
+        cr = __shfl_sync(0xFFFFFFFFu, cr, 0), co = __shfl_sync(0xFFFFFFFFu, co, 0), cs = __shfl_sync(0xFFFFFFFFu, cs, 0);
+        while (going) {
+            if (cs == 0) {
+                // lane i: is step i of a diagonal run from (cr, co) the step the reference takes at (cr - i, co - i)?
+                const int ri = cr - lane, oi = co - lane;
+                bool ok = ri >= 2 && oi >= 1 && ri != V - 1;  // the predecessor ri - 1 is not the start row (rank 0)
+                if (ok) {
+                    const uint4 rv = __ldg(reinterpret_cast<const uint4 *>(recs + ri));
+                    const RowRec rec{rv.x, rv.y, rv.z, rv.w};
+                    ok = (rec.npred_sym & 0xFFFFFFu) == 1u && rec.pred0_slot == ROW_PREV_IN_REGS;
+                    if (ok) {
+                        const int cur = val(ri, oi, 0), prev = val(ri - 1, oi - 1, 0);
+                        const bool me = (int)(rec.npred_sym >> 24) == (int)q[oi - 1];
+                        const int want = me ? cur : cur - x;
+                        ok = cur >= 0 && want >= 0 && prev == want;
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+                const int n = __ffs((int)~m) - 1;  // leading run of successes (32 when every lane succeeded: ~m == 0 -> ffs 0 -> -1)
+                const int run = n < 0 ? 32 : n;
+                if (run > 0) {
+                    if (pos < (uint32_t)run) {
+                        status = POASTA_ERR_UNSUPPORTED;
+                        break;
+                    }
+                    if (lane < run) out_r[pos - 1 - lane] = node_id[ri], out_q[pos - 1 - lane] = (uint32_t)(oi - 1);
+                    pos -= (uint32_t)run, cr -= run, co -= run;
                     continue;
                 }
-                if (pos == 0) {
-                    status = POASTA_ERR_UNSUPPORTED;
-                    break;
-                }
-                --pos;
-                if (cs == 0) out_r[pos] = node_id[cr], out_q[pos] = (uint32_t)(co - 1);
-                else if (cs == 2) out_r[pos] = POASTA_NONE, out_q[pos] = (uint32_t)(co - 1);
-                else out_r[pos] = node_id[cr], out_q[pos] = POASTA_NONE;
-                if (br == 0) break;  // predecessor is the start node (rank 0)
-                cr = br, co = bo, cs = bs;
             }
+            // one step with the full rule set (lane 0), exactly the reference's loop body
+            int stop = 0;
+            if (lane == 0) {
+                if (!step(cr, co, cs, br, bo, bs)) {
+                    stop = 1;
+                } else if (cs == 0 && bs != 0) {
+                    cr = br, co = bo, cs = bs;
+                } else if (pos == 0) {
+                    status = POASTA_ERR_UNSUPPORTED;
+                    stop = 1;
+                } else {
+                    --pos;
+                    if (cs == 0) out_r[pos] = node_id[cr], out_q[pos] = (uint32_t)(co - 1);
+                    else if (cs == 2) out_r[pos] = POASTA_NONE, out_q[pos] = (uint32_t)(co - 1);
+                    else out_r[pos] = node_id[cr], out_q[pos] = POASTA_NONE;
+                    if (br == 0) stop = 1;  // predecessor is the start node (rank 0)
+                    cr = br, co = bo, cs = bs;
+                }
+            }
+            stop = __shfl_sync(0xFFFFFFFFu, stop, 0);
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            status = __shfl_sync(0xFFFFFFFFu, status, 0);
+            cr = __shfl_sync(0xFFFFFFFFu, cr, 0), co = __shfl_sync(0xFFFFFFFFu, co, 0), cs = __shfl_sync(0xFFFFFFFFu, cs, 0);
+            if (stop) break;
         }
     }
-    P.n_pairs[a] = ad.out_cap - pos;
-    P.status[a] = status;
+    if (lane == 0) {
+        P.n_pairs[a] = ad.out_cap - pos;
+        P.status[a] = status;
+    }
 }
 
 }  // namespace poasta

@@ -25,7 +25,8 @@ for i in range(N):
     recs = synth.parse_fasta(synth.config2_family(f))
     queries.append(recs[rnd + (i // n_graphs) % (20 - rnd)][1])
     gidx.append(f)
-for rep in range(3):
+import os
+for rep in range(int(os.environ.get('PROBE_REPS', '3'))):
     t0 = time.perf_counter()
     res = align_batch(graphs, queries, gidx, tiebreak=TIEBREAK_DP)
     wall = time.perf_counter() - t0
