@@ -334,9 +334,12 @@ def main():
             dom_ms, tr = search_ms, measured_traffic("msa_engine_kernel" if cfg != 5 else "replay_kernel")
             n_dom = args.steps  # one engine launch per step (plus one per extra pass for suspended families)
         else:
-            dominant, dom_ms, tr = "dp_fill kernels", dp_ms, measured_traffic("dp_fill_warp_kernel")
+            dominant, dom_ms, tr = "dp_fill_packed_kernel + traceback_rows_kernel", dp_ms, measured_traffic("dp_fill_packed_kernel")
             n_dom = max(1, int(launches / world) // 4)
-        achieved = per_rank_cells * ALG_BYTES_PER_CU / (dom_ms / 1e3) / 1e9
+        # algorithmic bytes per cell update: 1 B (traceback budget of SURVEY.md 8d) for the search; the packed DP fill stores the M and D
+        # rows as u16 (4 B per cell update) instead of per-cell decision bits, and those rows ARE its traceback store
+        alg_bytes = ALG_BYTES_PER_CU if exact else 4.0
+        achieved = per_rank_cells * alg_bytes / (dom_ms / 1e3) / 1e9
         traffic = tr["dram_bytes_per_cu"] * per_rank_cells / n_dom if tr else None
         line = {
             "metric": "GCUPS", "value": gcups_dev, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -353,10 +356,13 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                          "traffic_note": (f"ncu dram__bytes_read+write = {tr['dram_bytes_per_cu']:.2f} B per cell update ({tr['capture']}), "
                                           "scaled to the average launch of this run") if tr else "no ncu capture",
-                         "note": "algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) x cells of the launch / launch duration "
-                                 "(CUDA events). In reference-exact mode the kernel is the order-exact search, a latency-bound state machine "
-                                 "(one dependent chain of memory round trips per in-flight alignment), not a streaming kernel: its HBM fraction "
-                                 "is small by construction (DESIGN.md section 4)"},
+                         "algorithmic_bytes_per_cu": alg_bytes,
+                         "note": ("algorithmic bytes = 1 B per cell update (SURVEY.md 8d traceback budget) x cells of the launch / launch duration "
+                                  "(CUDA events). In reference-exact mode the kernel is the order-exact search, a latency-bound state machine "
+                                  "(one dependent chain of memory round trips per in-flight alignment), not a streaming kernel: its HBM fraction "
+                                  "is small by construction (DESIGN.md section 4)") if exact else
+                                 ("algorithmic bytes = 4 B per cell update (M and D rows as u16, the traceback store of the packed kernel) x cells "
+                                  "/ duration of fill + traceback + scan (CUDA events, summed over the concurrent pipeline lanes)")},
             "clocks": clocks,
         }
         if exact and cfg != 5:
@@ -384,7 +390,10 @@ def main():
             del g2
             line["dp_only_mode"] = {"e2e_gcups": c2 / w2 / 1e9, "seqs_per_s": sum(len(x) for x in s2) / w2, "ms": w2 * 1e3,
                                     "kernel_gcups": c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9, "units": len(sub),
-                                    "note": "tiebreak=dp (DP fill + traceback kernels produce the alignments; host-side graph update) on half of "
+                                    "kernel_int_roofline_frac": (c2 / (min(k2, w2 * 1e3) / 1e3) / 1e12 * ALG_INT_OPS_PER_CU / line["int_roofline"]["peak"]
+                                                                 if "peak" in line.get("int_roofline", {}) else None),
+                                    "kernel_hbm_gbs": 4.0 * c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9,
+                                    "note": "tiebreak=dp (packed s16x2 DP fill + traceback kernels produce the alignments; host-side graph update) on half of "
                                             "step 0's batch after the timed region; kernel time is the sum over concurrent pipeline lanes"}
         if world == 1 and not args.no_cpu_baseline:
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)

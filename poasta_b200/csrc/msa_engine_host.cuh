@@ -211,11 +211,16 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             CK(cudaEventRecord(c.ev0, s));
             {
                 const dim3 grid((unsigned)(workers / wpc)), block(wpc * 32);
+                static const int carveout = getenv("POASTA_ENGINE_CARVEOUT") ? atoi(getenv("POASTA_ENGINE_CARVEOUT")) : -1;
+                auto launch_k = [&](auto kernel) {
+                    if (carveout >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+                    kernel<<<grid, block, 0, s>>>(E);
+                };
                 auto launch = [&](auto cell) {
                     using CellT = decltype(cell);
-                    if (prm.heuristic == 0) msa_engine_kernel<CellT, 0><<<grid, block, 0, s>>>(E);
-                    else if (prm.heuristic == 1) msa_engine_kernel<CellT, 1><<<grid, block, 0, s>>>(E);
-                    else msa_engine_kernel<CellT, 2><<<grid, block, 0, s>>>(E);
+                    if (prm.heuristic == 0) launch_k(msa_engine_kernel<CellT, 0>);
+                    else if (prm.heuristic == 1) launch_k(msa_engine_kernel<CellT, 1>);
+                    else launch_k(msa_engine_kernel<CellT, 2>);
                 };
                 if (cell16) launch(uint16_t{});
                 else launch(uint32_t{});

@@ -89,7 +89,10 @@ enum : int { RP_OK = 0, RP_EMPTY_QUEUE = 1, RP_NO_BACKTRACE = 2, RP_SCORE_WRAP =
 template <typename CellT> struct alignas(4 * sizeof(CellT)) Rec {
     CellT m, d, i, ep;
 };
-constexpr uint32_t QWIN = 64;  // priorities whose stack heads are kept in the fast window
+#ifndef RP_QWIN
+#define RP_QWIN 64
+#endif
+constexpr uint32_t QWIN = RP_QWIN;  // priorities whose stack heads are kept in the fast window (power of two)
 
 struct alignas(16) NodeA {
     uint32_t succ_off, bub_off;  // into Graph::succ / Graph::bub (quadruples)
