@@ -100,6 +100,10 @@ int poasta_last_batch_device_ms(double *device_ms);
 /* num_queued / num_visited / num_pruned summed over every alignment of the last poasta_msa_batch* on this thread
  * (reference-exact mode). */
 int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited, uint64_t *num_pruned);
+/* Which DP fill kernel the last chunk of the last DP-path call on this thread ran (a diagnostic for tests and benches; no
+ * reference counterpart): 0 none yet, 1 CTA-per-alignment (32-bit), 2 warp-per-alignment (32-bit, bit planes),
+ * 3 packed s16x2 warp-per-alignment, 4 packed s16x2 thread-block cluster (queries of 1024+ bases). */
+int poasta_last_dp_kernel(void);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Measured integer issue peaks of `device` in 10^12 lane-operations per second: 32-bit add, xor+min pairs (2 operations),

@@ -116,6 +116,11 @@ def last_batch_stats():
     return ms.value, nl.value, cells.value
 
 
+def last_dp_kernel():
+    """Which DP fill kernel the last DP-path call ran: 1 CTA, 2 warp (32-bit), 3 packed s16x2, 4 packed cluster (diagnostic)."""
+    return int(_lib.load().poasta_last_dp_kernel())
+
+
 def last_batch_search_ms():
     lib = _lib.load()
     ms = C.c_double()

@@ -11,13 +11,15 @@
 //     insertion: open before extend (the extend case resumes in Match state, gap_affine.rs:647-650);
 //   * the walk kernel applies gap_affine.rs:804-915 to those words.
 //
-// Kernel structure (this file is round-1 "v1": correct first; see DESIGN.md for the roofline plan):
-//   dp_fill_kernel   persistent CTAs (grid = resident slots); a CTA takes one alignment at a time,
-//                    rows = nodes in topological order, the query axis is split over the 256 threads
-//                    in 4-column groups (128-bit row loads/stores); the in-row insertion chain is a
-//                    block-wide prefix-min (warp shuffles + one smem hop); min/add-min recurrences use
-//                    the DPX intrinsics (__viaddmin_s32 / __vimin3_s32).
-//   traceback_kernel one thread per alignment walks the trace words and emits (rpos, qpos) pairs.
+// Kernels of the DP path (tiebreak = DP, and the score cross-check of the exact mode), chosen per batch in run_chunk:
+//   dp_fill_packed_kernel  (dp_packed_kernel.cuh) one warp per alignment, two 16-bit scores per register, DPX packed
+//                    instructions written as intrinsics (__vimin3_s16x2, __vmins2), row records staged by TMA bulk copies,
+//                    M / D rows stored as the traceback store; queries <= 1023, graphs over ACGT, scores provably < 0x5000.
+//   dp_fill_warp_kernel    (dp_warp_kernel.cuh) the 32-bit version with bit-plane traceback: same shape limits, any costs / symbols.
+//   dp_fill_kernel         (below) persistent CTAs, one alignment per CTA, the query axis split over 256 threads in 4-column
+//                    groups; for queries of 1024+ bases or in-degree > 1023. Its recurrences are plain min() / + in 32 bits
+//                    (ptxas fuses them into VIADDMNMX / VIMNMX3; no intrinsic is called here).
+//   traceback_rows_kernel / traceback_planes_kernel / traceback_kernel   the walkers matching the three fills.
 //   compact_kernel   packs the pairs of all alignments densely for one D2H copy.
 #include <cuda_runtime.h>
 
@@ -480,6 +482,7 @@ static std::mutex &device_call_mutex(int device) {
 static thread_local double tl_kernel_ms = 0, tl_search_ms = 0;
 static thread_local double tl_lane_max_ms = -1;  // msa batches: the largest per-lane sum of kernel time (lanes overlap on the device)
 static thread_local uint32_t tl_launches = 0;
+static thread_local int tl_dp_kernel = 0;  // poasta_last_dp_kernel
 static thread_local uint64_t tl_cells = 0;
 static thread_local uint64_t tl_h2d = 0, tl_d2h = 0;
 static thread_local uint64_t tl_engine_counts[3] = {0, 0, 0};  // queued, visited, pruned summed over the last msa batch (reference-exact mode)
@@ -529,21 +532,33 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     // packed s16x2 kernel (dp_packed_kernel.cuh) when the optimal score provably stays below its 16-bit "infinite" and the
     // insertion prefix-min offsets fit: every global alignment costs at most "delete a whole path, insert the whole query"
     static const bool force_s32 = getenv("POASTA_DP_KERNEL") && !strcmp(getenv("POASTA_DP_KERNEL"), "warp32");
-    const uint64_t worst_opt = 2ull * prm.gap_open + (uint64_t)prm.gap_extend * ((uint64_t)pb.max_V + pb.max_Q) + prm.mismatch;
-    const bool use_packed = use_warp && !force_s32 && pb.acgt_only && worst_opt < PK_INF && (uint64_t)prm.gap_extend * 1024 <= PK_KMAX;
-    const size_t per_slot = use_packed ? std::max<size_t>(16, (size_t)pb.max_n_stored * 32 * 128)
+    // (max_lmin = the longest of the graphs' SHORTEST start -> end paths: that many nodes are deleted, the whole query inserted)
+    const uint64_t worst_opt = 2ull * prm.gap_open + (uint64_t)prm.gap_extend * ((uint64_t)pb.max_lmin + pb.max_Q) + prm.mismatch;
+    const bool packed_ok = !force_s32 && !force_cta && pb.acgt_only && worst_opt < PK_INF && (uint64_t)prm.gap_extend * 1024 <= PK_KMAX &&
+                           pb.max_in_degree <= 1023;
+    const bool use_packed = use_warp && packed_ok;
+    // queries of 1024+ bases: a thread-block cluster of one-warp CTAs, one 1024-column segment each, linked through DSMEM
+    const uint32_t n_seg_max = (pb.max_W + 1023) / 1024;
+    const bool use_cluster = !use_warp && packed_ok && pb.max_W > (uint32_t)WARP_MAX_W && n_seg_max <= 8;
+    const unsigned cluster_ctas = n_seg_max <= 2 ? 2 : (n_seg_max <= 4 ? 4 : 8);
+    const size_t per_slot = use_cluster ? 16 : use_packed ? std::max<size_t>(16, (size_t)pb.max_n_stored * 32 * 128)
                             : use_warp ? (size_t)pb.max_store_cells * 2 * sizeof(int) : (size_t)pb.max_cells * 2 * sizeof(int);
     size_t slots = (size_t)c.n_sms * 4;  // CTA slots of the CTA-per-alignment kernel
-    if (use_packed) {
+    if (use_packed || use_cluster) {
         static bool attr_set[16] = {};
         if (!attr_set[c.device & 15]) {
-            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(dp_fill_packed_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_CLUSTER_SMEM));
             attr_set[c.device & 15] = true;
         }
+    }
+    if (use_cluster) {
+        slots = 4;  // no per-slot scratch: every row lives in the trace store
+    } else if (use_packed) {
         int ctas = 0;
-        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<false>, PK_WARPS * 32, PK_SMEM_BYTES);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<true>, PK_WARPS * 32, PK_SMEM_BYTES);
+        if (scores_only) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<false, false>, PK_WARPS * 32, PK_SMEM_BYTES);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_fill_packed_kernel<true, false>, PK_WARPS * 32, PK_SMEM_BYTES);
         slots = (size_t)c.n_sms * std::max(1, ctas) * PK_WARPS;
     } else if (use_warp) {               // warp slots: what the register file lets be resident
         int ctas = 0;
@@ -554,7 +569,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     slots = std::min<size_t>(slots, use_warp ? ((size_t)n + 3) / 4 * 4 : n);
     const size_t scratch_budget = std::max<size_t>(((size_t)8 << 30) / tl_lane_count, c.scratch.cap);
     while (slots > 4 && slots * per_slot > scratch_budget) slots = std::max<size_t>(4, slots / 2 / 4 * 4);
-    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(use_packed ? (scores_only ? 16 : pb.prow_halves * 2) : use_warp ? (scores_only ? 16 : pb.ptrace_words * 4) : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
+    if (!c.scratch.reserve(slots * per_slot) || !c.trace.reserve(use_cluster ? pb.prow_halves * 2 : use_packed ? (scores_only ? 16 : pb.prow_halves * 2) : use_warp ? (scores_only ? 16 : pb.ptrace_words * 4) : pb.trace_elems * tsz)) return POASTA_ERR_CUDA;  // only the warp kernel can skip the trace
     bool ok = c.graphs.reserve(pb.graphs.size() * sizeof(GraphDesc)) && c.alns.reserve(n * sizeof(AlnDesc)) &&
               c.node_sym.reserve(pb.node_sym.size()) && c.node_info.reserve(pb.node_info.size() * 4) &&
               c.node_id.reserve(pb.node_id.size() * 4) && c.ord_slot.reserve(pb.ord_slot.size() * 4) &&
@@ -562,7 +577,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
               c.pred_off.reserve(pb.pred_off.size() * 4) &&
               c.pred_rank.reserve(pb.pred_rank.size() * 4 + 4) && c.pred_slot.reserve(pb.pred_slot.size() * 4 + 4) &&
               c.queries.reserve(pb.queries.size() + 4) &&
-              c.scores.reserve(n * 4) && c.counter.reserve(4) && c.out_r.reserve(pb.out_elems * 4) &&
+              c.scores.reserve(n * 4) && c.counter.reserve(8) && c.out_r.reserve(pb.out_elems * 4) &&
               c.out_q.reserve(pb.out_elems * 4) && c.n_pairs.reserve(n * 4) && c.status.reserve(n * 4) &&
               c.offsets.reserve((n + 1) * 4);
     if (!ok) return POASTA_ERR_CUDA;
@@ -580,7 +595,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         CK(cudaMemcpyAsync(c.pred_slot.d, pb.pred_slot.data(), pb.pred_slot.size() * 4, cudaMemcpyHostToDevice, s));
     }
     if (!pb.queries.empty()) CK(cudaMemcpyAsync(c.queries.d, pb.queries.data(), pb.queries.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(c.counter.d, 0, 4, s));
+    CK(cudaMemsetAsync(c.counter.d, 0, 8, s));  // [0] work queue, [1] abort flag of the cluster kernel
     CK(cudaMemsetAsync(c.scores.d, 0x3F, n * 4, s));
     tl_h2d += pb.graphs.size() * sizeof(GraphDesc) + n * sizeof(AlnDesc) + pb.node_sym.size() + pb.node_info.size() * 4 +
               pb.node_id.size() * 4 + pb.pred_off.size() * 4 + pb.pred_rank.size() * 8 + pb.ord_slot.size() * 4 +
@@ -612,11 +627,24 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
     P.n_pairs = (uint32_t *)c.n_pairs.d;
     P.status = (int32_t *)c.status.d;
 
+    tl_dp_kernel = use_cluster ? 4 : use_packed ? 3 : use_warp ? 2 : 1;
     CK(cudaEventRecord(c.ev0, s));
-    if (use_packed) {
+    if (use_cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster_ctas, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(32), cfg.dynamicSmemBytes = PK_CLUSTER_SMEM, cfg.stream = s, cfg.attrs = at, cfg.numAttrs = 1;
+        cfg.gridDim = dim3(cluster_ctas);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, dp_fill_packed_kernel<true, true>, &cfg) != cudaSuccess || max_clusters < 1) max_clusters = 1;
+        const unsigned n_clusters = (unsigned)std::min<uint64_t>(n, (uint64_t)max_clusters);
+        cfg.gridDim = dim3(n_clusters * cluster_ctas);
+        CK(cudaLaunchKernelEx(&cfg, dp_fill_packed_kernel<true, true>, P));
+    } else if (use_packed) {
         const unsigned grid = (unsigned)(slots / PK_WARPS), block = PK_WARPS * 32;
-        if (scores_only) dp_fill_packed_kernel<false><<<grid, block, PK_SMEM_BYTES, s>>>(P);
-        else dp_fill_packed_kernel<true><<<grid, block, PK_SMEM_BYTES, s>>>(P);
+        if (scores_only) dp_fill_packed_kernel<false, false><<<grid, block, PK_SMEM_BYTES, s>>>(P);
+        else dp_fill_packed_kernel<true, false><<<grid, block, PK_SMEM_BYTES, s>>>(P);
     } else if (use_warp) {
         const unsigned grid = (unsigned)(slots / WARP_KERNEL_WARPS), block = WARP_KERNEL_WARPS * 32;
         if (scores_only) dp_fill_warp_kernel<false><<<grid, block, 0, s>>>(P);
@@ -647,7 +675,7 @@ static int run_chunk(DeviceContext &c, const PackedBatch &pb, const poasta_param
         return 0;
     }
     const unsigned tb_blocks = (n + 127) / 128;
-    if (use_packed) traceback_rows_kernel<<<(n + 3) / 4, 128, 0, s>>>(P);  // one warp per alignment
+    if (use_packed || use_cluster) traceback_rows_kernel<<<(n + 3) / 4, 128, 0, s>>>(P);  // one warp per alignment
     else if (use_warp) traceback_planes_kernel<<<tb_blocks, 128, 0, s>>>(P);
     else if (wide) traceback_kernel<uint32_t><<<tb_blocks, 128, 0, s>>>(P);
     else traceback_kernel<uint16_t><<<tb_blocks, 128, 0, s>>>(P);
@@ -1237,6 +1265,8 @@ int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited,
     if (num_pruned) *num_pruned = tl_engine_counts[2];
     return 0;
 }
+
+int poasta_last_dp_kernel(void) { return tl_dp_kernel; }
 
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = tl_h2d;

@@ -65,6 +65,7 @@ constexpr uint32_t ROW_PREV_IN_REGS = 0xFFFFFFFFu;
 struct PackedGraph {
     uint32_t V = 0, max_in_degree = 0, n_stored = 0, n_ord_rows = 0;
     bool acgt_only = true;  // every real node carries A, C, G or T (the packed kernel's symbol tables)
+    uint32_t lmin = 0;      // edges on the shortest start -> end path (bounds the optimal global score from above)
     std::vector<uint8_t> node_sym;
     std::vector<uint32_t> node_info, node_id, ord_slot, pred_off, pred_rank, pred_slot;
     std::vector<RowRec> rows;
@@ -112,6 +113,16 @@ struct PackedGraph {
             max_in_degree = std::max(max_in_degree, g.pred_off[v + 1] - g.pred_off[v]);
         }
         pred_off.push_back((uint32_t)pred_rank.size());
+        {
+            std::vector<uint32_t> &dist = rank_scratch;  // the rank table is no longer needed
+            dist.assign(V, 0xFFFFFFFFu);
+            for (uint32_t r = 0; r < V; ++r) {
+                if (node_info[r] & INFO_IS_START) dist[r] = 0;
+                for (uint32_t k = pred_off[r]; k < pred_off[r + 1]; ++k)
+                    if (dist[pred_rank[k]] != 0xFFFFFFFFu) dist[r] = std::min(dist[r], dist[pred_rank[k]] + 1);
+                if (node_info[r] & INFO_IS_END) lmin = dist[r] == 0xFFFFFFFFu ? V : dist[r];
+            }
+        }
         // rows read through the row store: every predecessor that is not the row just before its successor (that one is
         // still in registers when the successor is computed)
         for (uint32_t r = 0; r < V; ++r)
@@ -147,7 +158,7 @@ struct PackedBatch {
     uint64_t ptrace_words = 0;
     uint64_t prow_halves = 0;  // packed kernel's M / D row store
     uint32_t max_n_stored = 0; // max over alignments of the graph's n_stored
-    uint32_t max_V = 0, max_Q = 0;
+    uint32_t max_V = 0, max_Q = 0, max_lmin = 0;
     bool acgt_only = true;
     uint64_t out_elems = 0;
     uint64_t max_cells = 0;  // max over alignments of V * W
@@ -169,7 +180,7 @@ struct PackedBatch {
         rows.clear();
         queries.clear();
         trace_elems = ptrace_words = prow_halves = out_elems = max_cells = total_cells = max_store_cells = 0;
-        max_in_degree = max_n_stored = max_V = max_Q = 0;
+        max_in_degree = max_n_stored = max_V = max_Q = max_lmin = 0;
         acgt_only = true;
         max_W = 0;
     }
@@ -204,6 +215,7 @@ struct PackedBatch {
         pred_slot.insert(pred_slot.end(), pg.pred_slot.begin(), pg.pred_slot.end());
         max_in_degree = std::max(max_in_degree, gd.max_in_degree);
         acgt_only = acgt_only && pg.acgt_only;
+        max_lmin = std::max(max_lmin, pg.lmin);
         graphs.push_back(gd);
         return (uint32_t)graphs.size() - 1;
     }

@@ -62,22 +62,84 @@ __device__ __forceinline__ void pk_mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// ---- cluster mode: queries of 1024+ bases ------------------------------------------------------------------------
+// A thread-block CLUSTER of up to 8 one-warp CTAs shares one alignment: CTA s owns the columns [1024 s, 1024 s + 1024). Per row the
+// only values that cross a segment boundary are the predecessor row's M at the segment's last column (the diagonal term of the
+// next segment's first column) and the running insertion prefix-min; CTA s writes both into a ring in CTA s + 1's shared memory
+// through DSMEM (st.release.cluster on the sequence word) and CTA s + 1, working about one row behind, spins on its own shared
+// memory (ld.acquire.cluster). The consumer acknowledges through a counter in the producer's shared memory, so the ring never
+// overruns. Sequence numbers run on across alignments; no cluster-wide barrier is needed.
+constexpr int PK_RING = 32;
+struct PkMsg {
+    uint32_t left;  // packed pair whose high half is the predecessor row's M at the producer's last column
+    int pm;         // inclusive insertion prefix-min of all columns up to the producer's last one, in the producer's frame
+    uint32_t seq;   // row sequence number + 1 once the entry is valid
+    uint32_t pad;
+};
+constexpr int PK_CLUSTER_SMEM = PK_WARP_SMEM + PK_RING * (int)sizeof(PkMsg) + 16;
+constexpr uint32_t PK_SPIN_LIMIT = 1u << 27;  // a wait that lasts this many polls aborts the launch instead of hanging the GPU
+
+__device__ __forceinline__ void pk_st_release_cluster(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t pk_ld_acquire_cluster(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t pk_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t pk_cluster_id() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t pk_n_clusters() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+// generic address of `p` (a shared-memory address of this CTA) in CTA `rank` of the cluster
+template <typename T> __device__ __forceinline__ T *pk_map_rank(T *p, uint32_t rank) {
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<uint64_t>(p)), "r"(rank));
+    return reinterpret_cast<T *>(out);
+}
+
 // node symbols index the per-symbol tables; the host picks this kernel only for graphs over A, C, G, T (start / end rows carry no
 // symbol: their diagonal and deletion terms are infinite or symbol-free, so any table serves)
 __device__ __forceinline__ int pk_sym_index(int s) { return s == 'C' ? 1 : (s == 'G' ? 2 : (s == 'T' ? 3 : 0)); }
 
 // Row r of an alignment's store: lanes * 64 halves = [M: 4 chunks x lanes x 8 halves][D: the same]; as uint4: 8 * lanes per row.
-template <bool WRITE_ROWS>
-__global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchDev P) {
+// CLUSTER = false: PK_WARPS independent warps per CTA, one alignment each (queries <= 1023). CLUSTER = true: one warp per CTA, the
+// CTAs of a cluster are the 1024-column segments of one alignment (always WRITE_ROWS).
+template <bool WRITE_ROWS, bool CLUSTER>
+__global__ void __launch_bounds__(CLUSTER ? 32 : PK_WARPS * 32, CLUSTER ? 12 : 3) dp_fill_packed_kernel(BatchDev P) {
+    static_assert(!CLUSTER || WRITE_ROWS, "the cluster kernel keeps every row in the trace store");
     extern __shared__ uint4 pk_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = CLUSTER ? 0 : threadIdx.x >> 5;
+    constexpr int NW = CLUSTER ? 1 : PK_WARPS;  // warps sharing this CTA's dynamic shared memory
     const uint32_t worker = blockIdx.x * PK_WARPS + wib;
     uint4 *const tabE = pk_smem + (size_t)wib * (PK_TAB_WORDS / 4);  // [sym][chunk][lane] uint4 (4 pairs per chunk)
     uint4 *const tabN = tabE + 4 * 4 * 32;
     // the graph's row records (16 B per row: flags, predecessor summary, symbol) are staged through shared memory in tiles of
     // PK_TILE_ROWS rows by TMA bulk copies, two tiles ahead of the row being computed; lane 0 issues, an mbarrier per buffer signals
-    RowRec *const tile = reinterpret_cast<RowRec *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)PK_WARPS * PK_TAB_WORDS * 4) + (size_t)wib * 2 * PK_TILE_ROWS;
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)PK_WARPS * (PK_TAB_WORDS * 4 + 2 * PK_TILE_ROWS * 16)) + wib * 2;
+    RowRec *const tile = reinterpret_cast<RowRec *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)NW * PK_TAB_WORDS * 4) + (size_t)wib * 2 * PK_TILE_ROWS;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(pk_smem) + (size_t)NW * (PK_TAB_WORDS * 4 + 2 * PK_TILE_ROWS * 16)) + wib * 2;
+    // cluster mode: the incoming ring and the acknowledgement counter of the outgoing one
+    PkMsg *const ring = reinterpret_cast<PkMsg *>(reinterpret_cast<uint8_t *>(pk_smem) + PK_WARP_SMEM);
+    uint32_t *const acked = reinterpret_cast<uint32_t *>(ring + PK_RING);  // rows the NEXT segment has consumed (it writes this)
+    const uint32_t seg = CLUSTER ? pk_cluster_ctarank() : 0u;
+    uint32_t g_in = 0, g_out = 0;  // rows received from segment seg - 1 / sent to segment seg + 1 so far
+    if (CLUSTER) {
+        for (int i = lane; i < PK_RING; i += 32) ring[i].seq = 0;
+        if (lane == 0) *acked = 0;
+        __syncwarp();
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");  // rings are zero before anyone sends
+    }
     if (lane == 0) {
         pk_mbar_init(&bars[0]);
         pk_mbar_init(&bars[1]);
@@ -88,18 +150,27 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
     uint4 *const slot = reinterpret_cast<uint4 *>(P.scratch + (uint64_t)worker * P.scratch_stride);  // scores-only: compact row store
     const uint32_t x2 = (uint32_t)P.x * 0x10001u, oe2 = (uint32_t)P.oe * 0x10001u, e2 = (uint32_t)P.e * 0x10001u;
     const uint32_t o2 = (uint32_t)(P.oe - P.e) * 0x10001u;
-    const int j0 = lane * 32;
+    const int j0 = (int)seg * 1024 + lane * 32;  // first column of this lane
+    const int vlane = (int)seg * 32 + lane;      // lane index across the segments of a row
 
-    for (;;) {
+    for (uint32_t it = 0;; ++it) {
         uint32_t a = 0;
-        if (lane == 0) a = atomicAdd(P.counter, 1u);
-        a = __shfl_sync(0xFFFFFFFFu, a, 0);
+        if (CLUSTER) {
+            a = pk_cluster_id() + it * pk_n_clusters();  // static assignment: every CTA of the cluster derives the same alignment
+        } else {
+            if (lane == 0) a = atomicAdd(P.counter, 1u);
+            a = __shfl_sync(0xFFFFFFFFu, a, 0);
+        }
         if (a >= P.n_alns) break;
+        if (CLUSTER && *reinterpret_cast<volatile uint32_t *>(P.counter + 1)) break;  // another cluster gave up waiting
         const AlnDesc ad = P.alns[a];
         const GraphDesc gd = P.graphs[ad.graph];
         const int Q = (int)ad.Q, V = (int)gd.V;
-        const int nl = ((int)ad.W + 31) >> 5;  // lanes that own columns
-        const bool lane_active = lane < nl;
+        const int nl = ((int)ad.W + 31) >> 5;  // lanes that own columns, over all segments
+        const int n_seg = (nl + 31) >> 5;
+        if (CLUSTER && (int)seg >= n_seg) continue;  // this alignment needs fewer segments than the cluster has
+        const bool lane_active = vlane < nl;
+        const bool recv = CLUSTER && seg > 0, send = CLUSTER && (int)seg + 1 < n_seg;
         const uint8_t *q = P.queries + ad.query_base;
         const RowRec *rows = P.rows + gd.node_base;
         const uint32_t *prank = P.pred_rank + gd.pred_base, *pslot = P.pred_slot + gd.pred_base;
@@ -131,7 +202,8 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
         uint32_t K[16];  // (Wc - j) e per half, Wc = 32 nl: the offsets of the insertion prefix-min (always >= e)
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const uint32_t lo = (uint32_t)(32 * nl - (j0 + 2 * k)) * (uint32_t)P.e, hi = lo - (uint32_t)P.e;
+            // single warp: Wc = 32 nl; cluster: every segment uses its own frame Wc = 1024 (the carry is shifted by 1024 e per hop)
+            const uint32_t lo = (uint32_t)(CLUSTER ? 1024 - (lane * 32 + 2 * k) : 32 * nl - (j0 + 2 * k)) * (uint32_t)P.e, hi = lo - (uint32_t)P.e;
             K[k] = lane_active ? (lo | (hi << 16)) : 0u;
         }
 
@@ -176,7 +248,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
 #pragma unroll
                         for (int k = 0; k < 16; ++k) Am[k] = __vmins2(Am[k], Pm[k]), Ad[k] = __vmins2(Ad[k], Pd[k]);
                     } else if (lane_active) {
-                        const uint4 *src = store + (uint64_t)(WRITE_ROWS ? pr : pslot[kk]) * row_u4 + lane;
+                        const uint4 *src = store + (uint64_t)(WRITE_ROWS ? pr : pslot[kk]) * row_u4 + vlane;
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const uint4 m = src[t * nl], d = src[(4 + t) * nl];
@@ -194,6 +266,27 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
             // ---- diagonal, deletion, X = min(diagonal, D) ----
             uint32_t left = __shfl_up_sync(0xFFFFFFFFu, Pm[15], 1);  // its high half is column j0 - 1
             if (lane == 0) left = PK_INF2;
+            const uint32_t left_send = Pm[15];  // lane 31: the next segment's `left`
+            int pm_in = (int)PK_BIG;
+            bool abort_wait = false;
+            if (recv) {  // the row's message from segment seg - 1 (it runs about one row ahead)
+                if (lane == 0) {
+                    PkMsg *m = &ring[g_in % PK_RING];
+                    uint32_t polls = 0;
+                    while (pk_ld_acquire_cluster(&m->seq) != g_in + 1)
+                        if (++polls > PK_SPIN_LIMIT || (!(polls & 0xFFFF) && *reinterpret_cast<volatile uint32_t *>(P.counter + 1))) {
+                            abort_wait = true;
+                            break;
+                        }
+                    left = m->left;
+                    pm_in = m->pm;
+                    pk_st_release_cluster(pk_map_rank(acked, seg - 1), g_in + 1);  // the entry may be reused
+                }
+                pm_in = __shfl_sync(0xFFFFFFFFu, pm_in, 0);
+                // the producer's frame ends 1024 columns to the left of mine
+                pm_in = min(pm_in + 1024 * P.e, (int)PK_BIG);
+                ++g_in;
+            }
             uint32_t X[16];
             const int si = pk_sym_index(vs);
             if (is_end) {
@@ -222,7 +315,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
                     }
                 }
             }
-            if (is_start && lane == 0) X[0] &= 0xFFFF0000u;  // M(start, 0) = 0
+            if (is_start && vlane == 0) X[0] &= 0xFFFF0000u;  // M(start, 0) = 0
 
             // ---- insertion chain: prefix-min over the whole row ----
             // an insertion opens at column k only if the node has a successor that is `end` or mismatches q[k]
@@ -256,6 +349,30 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
             }
             int pm = __shfl_up_sync(0xFFFFFFFFu, incl, 1);  // exclusive prefix-min over all columns left of mine
             if (lane == 0) pm = (int)PK_BIG;
+            if (CLUSTER) pm = min(pm, pm_in);
+            if (send) {
+                if (lane == 31) {
+                    uint32_t polls = 0;
+                    while (g_out - pk_ld_acquire_cluster(acked) >= (uint32_t)PK_RING)  // the consumer is a whole ring behind
+                        if (++polls > PK_SPIN_LIMIT || (!(polls & 0xFFFF) && *reinterpret_cast<volatile uint32_t *>(P.counter + 1))) {
+                            abort_wait = true;
+                            break;
+                        }
+                    PkMsg *m = pk_map_rank(&ring[g_out % PK_RING], seg + 1);
+                    m->left = left_send;
+                    m->pm = min(incl, pm_in);
+                    pk_st_release_cluster(&m->seq, g_out + 1);
+                }
+                ++g_out;
+            }
+            if (CLUSTER && __any_sync(0xFFFFFFFFu, abort_wait)) {
+                if (lane == 0) {
+                    atomicExch(P.counter + 1, 1u);
+                    P.scores[a] = (uint32_t)INF;
+                    P.status[a] = POASTA_ERR_INTERNAL;
+                }
+                break;
+            }
             uint32_t pmv = (uint32_t)pm * 0x10001u;
 
             // ---- final M ----
@@ -271,7 +388,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
 
             // ---- store the row ----
             if (lane_active && (WRITE_ROWS || (inf & INFO_STORE))) {
-                uint4 *dst = store + (uint64_t)(WRITE_ROWS ? (uint32_t)r : (inf >> INFO_SLOT_SHIFT)) * row_u4 + lane;
+                uint4 *dst = store + (uint64_t)(WRITE_ROWS ? (uint32_t)r : (inf >> INFO_SLOT_SHIFT)) * row_u4 + vlane;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     dst[t * nl] = make_uint4(Pm[4 * t], Pm[4 * t + 1], Pm[4 * t + 2], Pm[4 * t + 3]);
@@ -290,6 +407,8 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 3) dp_fill_packed_kernel(BatchD
         }
         __syncwarp();
     }
+    // no CTA may leave while a neighbour can still write into its shared memory (acknowledgements, ring entries)
+    if (CLUSTER) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // gap_affine.rs:550-657 + 804-915 on the M / D rows written by dp_fill_packed_kernel<true>. One WARP per alignment.

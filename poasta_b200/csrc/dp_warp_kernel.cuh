@@ -8,7 +8,8 @@
 //   * symbol tests from per-lane 32-bit equality masks of the query (one pair per symbol and alignment);
 //   * the in-row insertion chain I[j] = o + j e + min_{k<j, openI(k)} (min(Mdiag, D)[k] - k e) as a sequential
 //     prefix-min over the lane's own columns plus ONE 5-step warp-shuffle prefix-min per row;
-//   * add-min recurrences through the DPX intrinsic __viaddmin_s32;
+//   * add / min recurrences in plain 32-bit arithmetic (ptxas fuses them into VIADDMNMX / VIMNMX3; the packed 16-bit kernel in
+//     dp_packed_kernel.cuh, which replaces this one whenever scores fit, calls the DPX intrinsics directly);
 //   * "infinite" is any value >= 2^28 (INF = 2^29): sums never overflow, so there is no clamping in the inner loops.
 // Traceback is stored as BIT PLANES: per (row, lane) eight 32-bit words
 //     [M<-diag, M<-D, M<-I, D<-open, D<-extend, I reachable, -, -]   (bit c = column 32 lane + c)

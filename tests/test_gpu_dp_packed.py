@@ -111,3 +111,57 @@ for r in align_batch([g], qs, [0] * len(qs), tiebreak=TIEBREAK_DP):
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append(r.stdout)
     assert outs[0] == outs[1] and outs[0].count("\n") == 20
+
+
+# ---- cluster mode: queries of 1024+ bases, one 1024-column segment per CTA of a thread-block cluster, carries through DSMEM ----
+def _check_cluster(g, queries, x=4, o=6, e=2, kernel=4):
+    from poasta_b200 import aligner
+    cfg = AffineMinGapCost(GapAffine(cost_mismatch=x, cost_gap_extend=e, cost_gap_open=o))
+    res = align_batch([g], queries, [0] * len(queries), cfg, tiebreak=TIEBREAK_DP)
+    assert aligner.last_dp_kernel() == kernel, f"the batch ran on DP kernel {aligner.last_dp_kernel()}, expected {kernel}"
+    for q, r in zip(queries, res):
+        sc, pairs, _ = H.dpmodel_align(g, q, x=x, o=o, e=e)
+        assert r.score == sc, (len(q), r.score, sc)
+        assert r.alignment == pairs, f"pairs differ from the dense model (Q = {len(q)})"
+
+
+def test_cluster_segment_boundaries():
+    """Query lengths around the 1024-column segment boundaries, 2 and 3 active segments in one launch (cluster of 4)."""
+    fa = synth.config2_family(61, n_seqs=4, root_len=2500, rate=0.05)
+    g = _graph(fa)
+    recs = synth.parse_fasta(fa)
+    root = recs[0][1]
+    _check_cluster(g, [root[:n] for n in (1024, 1025, 1055, 1056, 1500, 2046, 2047, 2048, 2049, 2400)] + [recs[3][1], recs[1][1][300:1900]])
+
+
+def test_cluster_of_eight():
+    """7 kb queries: 7 active segments in a cluster of 8; a short query in the same batch leaves six CTAs idle. Costs 2/3/1:
+    the packed kernels need the provable bound 2o + e (Lmin + Q) + x below 0x5000, which 14 k bases allow only at e = 1."""
+    fa = synth.config2_family(62, n_seqs=3, root_len=7000, rate=0.04)
+    g = _graph(fa)
+    recs = synth.parse_fasta(fa)
+    _check_cluster(g, [recs[2][1], recs[0][1][:4100], recs[1][1][:1030]], x=2, o=3, e=1)
+
+
+def test_long_query_outside_the_16_bit_bound_falls_back():
+    """The same 7 kb problem at the default costs (bound 28 k > 0x5000) must leave the packed kernels and still be right."""
+    fa = synth.config2_family(62, n_seqs=3, root_len=7000, rate=0.04)
+    g = _graph(fa)
+    recs = synth.parse_fasta(fa)
+    _check_cluster(g, [recs[2][1]], kernel=1)
+
+
+def test_cluster_config4_shape():
+    """Config-4 shape (16S-like 1.5 kb at 15 % divergence): every member against the growing graph, DP mode."""
+    from poasta_b200 import aligner
+    recs = synth.parse_fasta(synth.config4_family(n_seqs=6, root_len=1500, rate=0.15))
+    g = POAGraph()
+    for i, (name, seq) in enumerate(recs):
+        if g.is_empty():
+            g.add_alignment_with_weights(name, seq, None)
+            continue
+        dp = PoastaAligner(tiebreak=TIEBREAK_DP).align(g, seq)
+        dsc, dpairs, _ = H.dpmodel_align(g, seq)
+        assert dp.score == dsc and dp.alignment == dpairs, f"member {i}"
+        assert len(seq) < 1024 or aligner.last_dp_kernel() == 4
+        g.add_alignment_with_weights(name, seq, dpairs)
