@@ -247,7 +247,7 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
-    from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT, AffinePathAware, AlignmentType, aligner, align_batch, msa_batch
+    from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT, AffinePathAware, AlignmentType, POAGraph, aligner, align_batch, msa_batch
     from poasta_b200.sharding import step_family_range
 
     cfg = args.config
@@ -280,7 +280,9 @@ def main():
         def head(fa, n=3):
             parts = fa.split(b">")
             return b">".join(parts[:n + 1])
-        warm_batches = [[head(f) for f in make_units(cfg, step_family_range(args.steps + w, rank, world, F)[0], F, args)]
+        # (DP-only mode: a step takes about a second, so its warm-up batches are full ones and size every buffer the timed steps use)
+        cut = head if tiebreak == TIEBREAK_EXACT else (lambda fa: fa)
+        warm_batches = [[cut(f) for f in make_units(cfg, step_family_range(args.steps + w, rank, world, F)[0], F, args)]
                         for w in range(n_warm_batches)] if cfg != 4 else [[head(batches[0][0], 4)]]
 
         def step(batch):
@@ -292,11 +294,16 @@ def main():
             crit = aligner.last_batch_device_ms()
             h2d, d2h = aligner.last_batch_io()
             nseq = sum(len(s) for s in scores)
-            del graphs
+            fill = aligner.last_batch_fill_ms() if aligner.last_msa_path() == 2 else (0.0, 0)
+            dp_fill[0] += fill[0]
+            dp_fill[1] += fill[1]
+            POAGraph.free_many(graphs)  # the finished graphs go back on several host threads (inside the timed region)
             return [wall, kms, sms, launches, cells, nseq, h2d, d2h, crit]
 
+    dp_fill = [0.0, 0]  # DP-only device pipeline: milliseconds and number of the fill launches alone (this rank)
     for w in range(args.warmup):
         step(warm_batches[w % len(warm_batches)])
+    dp_fill[0], dp_fill[1] = 0.0, 0
 
     def sync():
         torch.cuda.synchronize()
@@ -333,6 +340,10 @@ def main():
             dominant = "msa_engine_kernel (persistent: index build + order-exact search + graph update)" if cfg != 5 else "replay_kernel (order-exact search)"
             dom_ms, tr = search_ms, measured_traffic("msa_engine_kernel" if cfg != 5 else "replay_kernel")
             n_dom = args.steps  # one engine launch per step (plus one per extra pass for suspended families)
+        elif dp_fill[1]:
+            # device-resident DP rounds: the fill launches are timed alone (CUDA events around each launch, this rank's)
+            dominant, dom_ms, tr = "dp_fill_packed_kernel (device-resident DP rounds; fill launches timed alone)", dp_fill[0], measured_traffic("dp_fill_packed_kernel")
+            n_dom = dp_fill[1]
         else:
             dominant, dom_ms, tr = "dp_fill_packed_kernel + traceback_rows_kernel", dp_ms, measured_traffic("dp_fill_packed_kernel")
             n_dom = max(1, int(launches / world) // 4)
@@ -344,7 +355,7 @@ def main():
         line = {
             "metric": "GCUPS", "value": gcups_dev, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u16" if exact else "s32", "data": "synthetic",
+            "dtype": "u16" if exact else ("s16x2" if dp_fill[1] else "s32"), "data": "synthetic",
             "config": workload_config(cfg, args, F, world),
             "seqs_per_s": nseq / wall_max,
             "device_ms_per_step": {"dp_fill+traceback": dp_ms / args.steps, "engine_or_search": search_ms / args.steps,
@@ -362,7 +373,8 @@ def main():
                                   "(one dependent chain of memory round trips per in-flight alignment), not a streaming kernel: its HBM fraction "
                                   "is small by construction (DESIGN.md section 4)") if exact else
                                  ("algorithmic bytes = 4 B per cell update (M and D rows as u16, the traceback store of the packed kernel) x cells "
-                                  "/ duration of fill + traceback + scan (CUDA events, summed over the concurrent pipeline lanes)")},
+                                  "/ duration of " + ("the fill launches alone (CUDA events around each launch)" if dp_fill[1] else
+                                                      "fill + traceback + scan (CUDA events, summed over the concurrent pipeline lanes)"))},
             "clocks": clocks,
         }
         if exact and cfg != 5:
@@ -387,14 +399,15 @@ def main():
             g2, s2, c2 = msa_batch(sub, device=local, tiebreak=TIEBREAK_DP)
             w2 = time.perf_counter() - t0
             k2, _, _ = aligner.last_batch_stats()
-            del g2
+            POAGraph.free_many(g2)
             line["dp_only_mode"] = {"e2e_gcups": c2 / w2 / 1e9, "seqs_per_s": sum(len(x) for x in s2) / w2, "ms": w2 * 1e3,
                                     "kernel_gcups": c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9, "units": len(sub),
                                     "kernel_int_roofline_frac": (c2 / (min(k2, w2 * 1e3) / 1e3) / 1e12 * ALG_INT_OPS_PER_CU / line["int_roofline"]["peak"]
                                                                  if "peak" in line.get("int_roofline", {}) else None),
                                     "kernel_hbm_gbs": 4.0 * c2 / (min(k2, w2 * 1e3) / 1e3) / 1e9,
-                                    "note": "tiebreak=dp (packed s16x2 DP fill + traceback kernels produce the alignments; host-side graph update) on half of "
-                                            "step 0's batch after the timed region; kernel time is the sum over concurrent pipeline lanes"}
+                                    "pipeline": {1: "engine", 2: "device-resident DP rounds", 3: "per-round host pipeline"}.get(aligner.last_msa_path()),
+                                    "note": "tiebreak=dp (packed s16x2 DP fill + traceback kernels produce the alignments; graph packing and update on "
+                                            "the device too) on half of step 0's batch after the timed region; kernel time = all rounds on the device"}
         if world == 1 and not args.no_cpu_baseline:
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
             if cfg == 5:

@@ -104,6 +104,13 @@ int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited,
  * reference counterpart): 0 none yet, 1 CTA-per-alignment (32-bit), 2 warp-per-alignment (32-bit, bit planes),
  * 3 packed s16x2 warp-per-alignment, 4 packed s16x2 thread-block cluster (queries of 1024+ bases). */
 int poasta_last_dp_kernel(void);
+/* Which pipeline the last poasta_msa_batch* on this thread took (diagnostic): 0 none yet, 1 the reference-exact engine (one
+ * persistent kernel, everything on the device), 2 the device-resident DP-only rounds (tiebreak = 1: pack, fill, traceback and graph
+ * update on the device), 3 the per-round host pipeline of the DP-only mode (inputs the packed kernels do not cover, ends-free). */
+int poasta_last_msa_path(void);
+/* Device-resident DP-only rounds of the last poasta_msa_batch* on this thread: milliseconds of the dp_fill_packed_kernel launches
+ * alone (CUDA events around each launch) and their number - the dominant kernel of that pipeline, for roofline figures. */
+int poasta_last_batch_fill_ms(double *fill_ms, uint32_t *n_fill_launches);
 /* Host<->device bytes copied by the last poasta_align_batch / poasta_msa_batch* on this thread. */
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Measured integer issue peaks of `device` in 10^12 lane-operations per second: 32-bit add, xor+min pairs (2 operations),
@@ -116,6 +123,9 @@ typedef struct poasta_graph poasta_graph; /* opaque POAGraph<u32> */
 
 poasta_graph *poasta_graph_new(void);                                  /* POAGraph::new  poa.rs:100 */
 void poasta_graph_free(poasta_graph *g);
+/* Frees n graphs (the handles a poasta_msa_batch call returned) on n_threads host threads (0 = as many as the host has, at most 16)
+ * and nulls the entries. */
+void poasta_graph_free_many(poasta_graph **graphs, uint32_t n, uint32_t n_threads);
 uint32_t poasta_graph_node_count(const poasta_graph *g);               /* poa.rs:399 */
 uint32_t poasta_graph_node_count_with_start_and_end(const poasta_graph *g);
 uint32_t poasta_graph_edge_count(const poasta_graph *g);               /* poa.rs:409 */

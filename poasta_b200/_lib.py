@@ -38,8 +38,8 @@ class Result(C.Structure):
 
 # every symbol include/poasta_b200.h declares
 EXPORTS = [
-    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_dp_kernel", "poasta_last_batch_io", "poasta_last_batch_search_counts", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
-    "poasta_graph_new", "poasta_graph_free", "poasta_graph_node_count",
+    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_dp_kernel", "poasta_last_msa_path", "poasta_last_batch_fill_ms", "poasta_last_batch_io", "poasta_last_batch_search_counts", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
+    "poasta_graph_new", "poasta_graph_free", "poasta_graph_free_many", "poasta_graph_node_count",
     "poasta_graph_node_count_with_start_and_end", "poasta_graph_edge_count",
     "poasta_graph_num_sequences", "poasta_graph_add_alignment", "poasta_graph_get_view",
     "poasta_graph_aligned_nodes", "poasta_graph_to_fasta", "poasta_graph_to_gfa", "poasta_graph_to_dot",
@@ -62,6 +62,8 @@ def load():
     vp, u32p, u8p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
     lib.poasta_graph_new.restype = vp
     lib.poasta_graph_free.argtypes = [vp]
+    lib.poasta_graph_free_many.argtypes = [C.POINTER(vp), C.c_uint32, C.c_uint32]
+    lib.poasta_graph_free_many.restype = None
     for f in ("poasta_graph_node_count", "poasta_graph_node_count_with_start_and_end",
               "poasta_graph_edge_count", "poasta_graph_num_sequences"):
         getattr(lib, f).argtypes = [vp]

@@ -121,6 +121,18 @@ def last_dp_kernel():
     return int(_lib.load().poasta_last_dp_kernel())
 
 
+def last_msa_path():
+    """Pipeline of the last msa_batch: 1 reference-exact engine, 2 device-resident DP rounds, 3 per-round host pipeline (diagnostic)."""
+    return int(_lib.load().poasta_last_msa_path())
+
+
+def last_batch_fill_ms():
+    """(milliseconds, launches) of the DP fill kernel alone in the last device-resident DP-only build."""
+    ms, n = C.c_double(), C.c_uint32()
+    _lib.load().poasta_last_batch_fill_ms(C.byref(ms), C.byref(n))
+    return ms.value, n.value
+
+
 def last_batch_search_ms():
     lib = _lib.load()
     ms = C.c_double()

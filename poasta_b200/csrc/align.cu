@@ -483,6 +483,9 @@ static thread_local double tl_kernel_ms = 0, tl_search_ms = 0;
 static thread_local double tl_lane_max_ms = -1;  // msa batches: the largest per-lane sum of kernel time (lanes overlap on the device)
 static thread_local uint32_t tl_launches = 0;
 static thread_local int tl_dp_kernel = 0;  // poasta_last_dp_kernel
+static thread_local int tl_msa_path = 0;   // poasta_last_msa_path
+static thread_local double tl_fill_ms = 0;  // poasta_last_batch_fill_ms
+static thread_local uint32_t tl_fill_launches = 0;
 static thread_local uint64_t tl_cells = 0;
 static thread_local uint64_t tl_h2d = 0, tl_d2h = 0;
 static thread_local uint64_t tl_engine_counts[3] = {0, 0, 0};  // queued, visited, pruned summed over the last msa batch (reference-exact mode)
@@ -1267,6 +1270,12 @@ int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited,
 }
 
 int poasta_last_dp_kernel(void) { return tl_dp_kernel; }
+int poasta_last_msa_path(void) { return tl_msa_path; }
+int poasta_last_batch_fill_ms(double *fill_ms, uint32_t *n_fill_launches) {
+    if (fill_ms) *fill_ms = tl_fill_ms;
+    if (n_fill_launches) *n_fill_launches = tl_fill_launches;
+    return 0;
+}
 
 int poasta_last_batch_io(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = tl_h2d;
@@ -1428,8 +1437,11 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
     if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
     tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
-    if (params->tiebreak == 0) {
-        // reference-exact builds run entirely on the device (msa_engine.cuh): sequences in, finished graphs out
+    static const bool dp_host_only = getenv("POASTA_DP_HOST") != nullptr || getenv("POASTA_DP_KERNEL") != nullptr;
+    tl_msa_path = 0;
+    if (params->tiebreak == 0 || (params->mode == 0 && !dp_host_only)) {
+        // reference-exact builds run entirely on the device (msa_engine.cuh): sequences in, finished graphs out; so do DP-only
+        // builds whose inputs the packed kernels cover (msa_dp_device.cuh) - the others fall through to the per-round host pipeline
         DeviceContext &c = ctx_for(device);
         int rc = c.init(device);
         if (rc) return rc;
@@ -1460,14 +1472,20 @@ int poasta_msa_batch_into(int device, poasta_graph **graphs, const char *const *
             in[f] = EngineFamilyIn{graphs[f], &recs[f], scores_out ? scores_out + base : nullptr};
             base += recs[f].size();
         }
-        EngineStats st;
-        static EngineBuffers ebs[MAX_DEVICES];
-        rc = msa_engine_run(c, ebs[device], in, *params, st, host_threads);
-        tl_search_ms = st.kernel_ms, tl_lane_max_ms = st.kernel_ms, tl_launches = st.launches, tl_cells = st.cells;
-        tl_engine_counts[0] = st.queued, tl_engine_counts[1] = st.visited, tl_engine_counts[2] = st.pruned;
-        if (cells_out) *cells_out = st.cells;
-        return rc;
+        if (params->tiebreak == 0 || dp_device_eligible(in, *params)) {
+            EngineStats st;
+            static EngineBuffers ebs[MAX_DEVICES];
+            static DpBuffers dbs[MAX_DEVICES];
+            rc = msa_engine_run(c, ebs[device], dbs[device], in, *params, st, host_threads);
+            tl_lane_max_ms = st.kernel_ms, tl_launches = st.launches, tl_cells = st.cells;
+            if (params->tiebreak == 0) tl_search_ms = st.kernel_ms, tl_msa_path = 1;
+            else tl_kernel_ms = st.kernel_ms, tl_msa_path = 2, tl_fill_ms = st.fill_ms, tl_fill_launches = st.fill_launches;
+            tl_engine_counts[0] = st.queued, tl_engine_counts[1] = st.visited, tl_engine_counts[2] = st.pruned;
+            if (cells_out) *cells_out = st.cells;
+            return rc;
+        }
     }
+    tl_msa_path = 3;
     std::vector<size_t> score_base(n_families + 1, 0);
     for (uint32_t f = 0; f < n_families; ++f) {
         size_t n = 0;

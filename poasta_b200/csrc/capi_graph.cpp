@@ -1,5 +1,7 @@
 // C ABI: POAGraph handle + readers/writers (include/poasta_b200.h, host-only half).
 // Reference interfaces replaced: graphs/poa.rs:96-382, io/fasta.rs:69, io/graph.rs:24-103,245-502.
+#include <atomic>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -43,6 +45,27 @@ extern "C" {
 
 poasta_graph *poasta_graph_new(void) { return new (std::nothrow) poasta_graph(); }
 void poasta_graph_free(poasta_graph *g) { delete g; }
+void poasta_graph_free_many(poasta_graph **graphs, uint32_t n, uint32_t n_threads) {
+    // a finished 20 x 1 kb graph owns a few thousand small vectors (aligned-node lists, sequence ids per edge): freeing the
+    // thousands of graphs a batch returns is worth spreading over the host cores
+    if (!graphs || n == 0) return;
+    unsigned nt = n_threads ? n_threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n < 64 || nt <= 1) {
+        for (uint32_t i = 0; i < n; ++i) delete graphs[i], graphs[i] = nullptr;
+        return;
+    }
+    std::atomic<uint32_t> cursor{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t i0 = cursor.fetch_add(16);
+            if (i0 >= n) break;
+            for (uint32_t i = i0; i < std::min(n, i0 + 16); ++i) delete graphs[i], graphs[i] = nullptr;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+}
 uint32_t poasta_graph_node_count(const poasta_graph *g) { return g->g.node_count(); }
 uint32_t poasta_graph_node_count_with_start_and_end(const poasta_graph *g) { return g->g.node_count_with_start_and_end(); }
 uint32_t poasta_graph_edge_count(const poasta_graph *g) { return g->g.edge_count(); }

@@ -76,6 +76,9 @@ inline bool download(Family *f, uint8_t *chunk_arena, POAGraph &g, const std::ve
         nd.symbol = s.sym[n];
         nd.head[0] = s.head_out[n], nd.head[1] = s.head_in[n];
         nd.aligned_nodes.clear();
+        size_t n_al = 0;  // one exact allocation per list (a finished graph holds thousands of these small vectors)
+        for (uint32_t k = s.al_head[n]; k != NIL; k = s.al_next[k]) ++n_al;
+        nd.aligned_nodes.reserve(n_al);
         for (uint32_t k = s.al_head[n]; k != NIL; k = s.al_next[k]) nd.aligned_nodes.push_back(s.al_node[k]);
     }
     g.edges.resize(f->n_edge_slots);
@@ -86,6 +89,9 @@ inline bool download(Family *f, uint8_t *chunk_arena, POAGraph &g, const std::ve
         ed.vacant = s.e_src[e] == NIL;
         ed.weight = s.e_weight[e];
         ed.sequence_ids.clear();
+        size_t n_id = 0;
+        for (uint32_t k = s.e_sid_head[e]; k != NIL; k = s.sid_next[k]) ++n_id;
+        ed.sequence_ids.reserve(n_id);
         for (uint32_t k = s.e_sid_head[e]; k != NIL; k = s.sid_next[k]) ed.sequence_ids.push_back(s.sid_val[k]);
     }
     g.free_edge = f->free_edge;

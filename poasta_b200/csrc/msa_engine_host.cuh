@@ -19,7 +19,8 @@ struct EngineFamilyIn {
 struct EngineStats {
     uint64_t cells = 0, queued = 0, visited = 0, pruned = 0;
     double kernel_ms = 0;
-    uint32_t launches = 0, passes = 0;
+    double fill_ms = 0;  // DP-only mode: the fill launches alone
+    uint32_t launches = 0, passes = 0, fill_launches = 0;
 };
 
 // worker scratch layout for given capacities
@@ -48,9 +49,17 @@ struct WorkerLayout {
     }
 };
 
+}  // namespace poasta
+
+#include "msa_dp_device.cuh"
+
+namespace poasta {
+
 // Progressive builds of `n` families on one device. Families are processed in chunks that fit the arena budget.
-static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<EngineFamilyIn> &fams_in, const poasta_params &prm, EngineStats &st,
-                          unsigned host_threads) {
+// prm.tiebreak == 0: the reference-exact engine (msa_engine.cuh). prm.tiebreak == 1 (the caller has checked dp_device_eligible):
+// the DP-only rounds of msa_dp_device.cuh on the same arenas. Upload and download are shared.
+static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, std::vector<EngineFamilyIn> &fams_in, const poasta_params &prm,
+                          EngineStats &st, unsigned host_threads) {
     CK(cudaSetDevice(c.device));
     cudaStream_t s = c.stream;
     size_t free_b = 0, total_b = 0;
@@ -61,12 +70,16 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
     const uint64_t worker_budget = (uint64_t)(worker_fraction * (double)total_b);
     const uint64_t m = std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend);
 
+    static const bool phase_timing = getenv("POASTA_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_upload = 0, t_device = 0, t_copy_back = 0, t_convert = 0;
     size_t next = 0;
     std::vector<dg::Family> hf;
     std::vector<uint64_t> seq_off;
     std::vector<uint32_t> seq_len, tickets, chunk_ids;
     while (next < fams_in.size()) {
         // ---- one chunk: families [next, end) whose arenas fit the budget ----
+        const double t_chunk0 = now();
         hf.clear(), seq_off.clear(), seq_len.clear(), chunk_ids.clear();
         uint64_t arena_bytes = 0, seq_bytes = 0;
         uint32_t Qmax = 0, V0max = 2, n_records = 0;
@@ -141,9 +154,15 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
         CK(cudaMemcpyAsync(eb.fams.d, hf.data(), (size_t)nf * sizeof(dg::Family), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(eb.seq_out.d, 0, (size_t)n_records * SEQ_OUT_WORDS * 4, s));
 
+        const double t_chunk1 = now();
+        if (prm.tiebreak != 0) {
+            const int rc = msa_dp_rounds(c, eb, db, hf, n_records, seq_bytes, seq_len, prm, st);
+            if (rc) return rc;
+        }
+        if (prm.tiebreak == 0) db.trace.release();  // the DP-only mode's row store would take the memory the worker slabs are sized for
         // ---- passes: common-case workers first, larger ones for the families that were suspended ----
-        std::vector<uint32_t> todo(nf);  // family ids (chunk-local) still to run, with the records they have left
-        for (uint32_t i = 0; i < nf; ++i) todo[i] = i;
+        std::vector<uint32_t> todo(prm.tiebreak != 0 ? 0 : nf);  // family ids (chunk-local) still to run, with the records they have left
+        for (uint32_t i = 0; i < (uint32_t)todo.size(); ++i) todo[i] = i;
         std::vector<uint32_t> left(nf);
         for (uint32_t i = 0; i < nf; ++i) left[i] = hf[i].n_seqs;
         // largest V a 16-bit table can carry: (V + Q + 4) * m + o < CELL16_LIMIT
@@ -252,6 +271,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             }
         }
         // ---- download: headers, then the used parts of the arenas, packed on the device ----
+        const double t_chunk2 = now();
         if (!eb.h_fams.reserve((size_t)nf * sizeof(dg::Family)) || !eb.h_seq_out.reserve((size_t)n_records * SEQ_OUT_WORDS * 4)) return POASTA_ERR_CUDA;
         CK(cudaMemcpyAsync(eb.h_fams.h, eb.fams.d, (size_t)nf * sizeof(dg::Family), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(eb.h_seq_out.h, eb.seq_out.d, (size_t)n_records * SEQ_OUT_WORDS * 4, cudaMemcpyDeviceToHost, s));
@@ -272,6 +292,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
         ++st.launches;
         tl_d2h += poff[nf] + (uint64_t)nf * sizeof(dg::Family) + (uint64_t)n_records * SEQ_OUT_WORDS * 4;
         // ---- back into the std::vector graphs (host threads; the reference's toposort runs here, poa.rs:360) ----
+        const double t_chunk3 = now();
         const uint32_t *so = (const uint32_t *)eb.h_seq_out.h;
         std::atomic<int> err{0};
         std::atomic<uint32_t> cursor{0};
@@ -313,6 +334,7 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
             for (auto &t : pool) t.join();
         }
         for (const EngineStats &ps : part) st.cells += ps.cells, st.queued += ps.queued, st.visited += ps.visited, st.pruned += ps.pruned;
+        t_upload += t_chunk1 - t_chunk0, t_device += t_chunk2 - t_chunk1, t_copy_back += t_chunk3 - t_chunk2, t_convert += now() - t_chunk3;
         static const bool timing2 = getenv("POASTA_TIMING") != nullptr;
         if (timing2) {  // where the kernel's time went: busy share of the worker slots, longest family chain, search share of a round
             double busy = 0, search = 0, longest = 0;
@@ -330,6 +352,9 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, std::vector<Engin
         }
         if (err) return err;
     }
+    if (phase_timing)
+        fprintf(stderr, "poasta_b200 msa phases: upload %.3f s, device %.3f s, copy back %.3f s (%.1f MB), host graphs %.3f s (%u threads)\n", t_upload,
+                t_device, t_copy_back, (double)tl_d2h / 1e6, t_convert, host_threads);
     return 0;
 }
 

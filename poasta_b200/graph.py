@@ -44,6 +44,17 @@ class POAGraph:
             self._lib.poasta_graph_free(self._h)
             self._h = None
 
+    @staticmethod
+    def free_many(graphs, threads=0):
+        """Frees the graphs of a batch on several host threads (``poasta_graph_free_many``); the objects become unusable."""
+        hs = [g for g in graphs if getattr(g, "_h", None)]
+        if not hs:
+            return
+        arr = (C.c_void_p * len(hs))(*[g._h if isinstance(g._h, int) else g._h.value for g in hs])
+        for g in hs:
+            g._h = None
+        _lib.load().poasta_graph_free_many(arr, len(hs), threads)
+
     # -- graphs/poa.rs:114, 399-420 --
     def is_empty(self):
         return self.node_count() == 0

@@ -11,6 +11,7 @@
 #include "../../oracle/astar_oracle.hpp"
 #include "../../poasta_b200/csrc/device_batch.hpp"
 #include "../../poasta_b200/csrc/dev_graph_host.hpp"
+#include "../../poasta_b200/csrc/dev_dp_pack.hpp"
 #include "../../poasta_b200/csrc/dev_index.hpp"
 #include "../../poasta_b200/csrc/flatten.hpp"
 #include "../../poasta_b200/csrc/poa_io.hpp"
@@ -122,6 +123,45 @@ int devgraph_host_check(const char *fasta, size_t fasta_len, const uint8_t *grap
                 if (memcmp(w.path_off, si.path_off.data(), (size_t)(V + 1) * 4)) FAIL("round %zu: path_off differs", i);
                 if (w.n_path != si.path_rem.size() || memcmp(w.path_rem, si.path_rem.data(), si.path_rem.size() * 4))
                     FAIL("round %zu: path_rem differs", i);
+            }
+            // DP packing (dev_dp_pack.hpp, the DP-only mode's per-round step): device code on the host vs PackedGraph::build.
+            // The two use different topological orders, so everything is compared in node-id space.
+            {
+                const uint32_t E = view.pred_off[V];
+                dg::DpPackCaps pc{fam.n_nodes, fam.live_edges};
+                std::vector<uint8_t> pscratch(dg::DpPackLayout(pc).total, 0xCD);
+                dg::DpPackScratch pw(pscratch.data(), pc);
+                std::vector<RowRec> rows(V);
+                std::vector<uint32_t> node_id(V), pred_off(V + 1), pred_rank(E + 1);
+                std::vector<uint8_t> node_sym(V);
+                const uint32_t pred_base = 7;
+                dg::DpPackOut po{rows.data(), node_id.data(), node_sym.data(), pred_off.data(), pred_rank.data(), pred_base};
+                uint32_t maxdeg = 0;
+                if (int rc = dg::dp_pack(s, pw, po, &maxdeg, 0, 1, HostSync{})) FAIL("round %zu: dp_pack rc %d", i, rc);
+                PackedGraph pg;
+                std::vector<uint32_t> rs;
+                pg.build(view, rs);
+                if (maxdeg != pg.max_in_degree) FAIL("round %zu: dp_pack max in-degree %u vs %u", i, maxdeg, pg.max_in_degree);
+                if (node_id[0] != view.start_node || node_id[V - 1] != view.end_node) FAIL("round %zu: dp_pack start / end ranks", i);
+                std::vector<uint32_t> host_rank(V, 0xFFFFFFFFu), seen(V, 0);
+                for (uint32_t r = 0; r < V; ++r) host_rank[pg.node_id[r]] = r;
+                if (pred_off[0] != pred_base || pred_off[V] != pred_base + E) FAIL("round %zu: dp_pack pred_off ends", i);
+                for (uint32_t r = 0; r < V; ++r) {
+                    const uint32_t v = node_id[r];
+                    if (v >= V || seen[v]++) FAIL("round %zu: dp_pack node_id is not a permutation", i);
+                    const uint32_t hr = host_rank[v];
+                    if (node_sym[r] != pg.node_sym[hr]) FAIL("round %zu: dp_pack symbol of node %u", i, v);
+                    if ((rows[r].info & 0xFFF) != (pg.rows[hr].info & 0xFFF)) FAIL("round %zu: dp_pack info of node %u: %x vs %x", i, v, rows[r].info, pg.rows[hr].info);
+                    if (rows[r].npred_sym != pg.rows[hr].npred_sym) FAIL("round %zu: dp_pack npred_sym of node %u", i, v);
+                    const uint32_t np = rows[r].npred_sym & 0xFFFFFFu, b = pred_off[r] - pred_base, hb = pg.pred_off[hr];
+                    if (rows[r].pred_begin != b || pred_off[r + 1] - pred_off[r] != np) FAIL("round %zu: dp_pack pred range of node %u", i, v);
+                    for (uint32_t k = 0; k < np; ++k) {
+                        if (pred_rank[b + k] >= r) FAIL("round %zu: dp_pack order is not topological at node %u", i, v);
+                        if (node_id[pred_rank[b + k]] != pg.node_id[pg.pred_rank[hb + k]]) FAIL("round %zu: dp_pack predecessor %u of node %u", i, k, v);
+                    }
+                    const bool prev = np == 1 && pred_rank[b] + 1 == r;
+                    if ((rows[r].pred0_slot == ROW_PREV_IN_REGS) != prev) FAIL("round %zu: dp_pack previous-row flag of node %u", i, v);
+                }
             }
             oracle::AstarResult r = oracle::astar_align(view, q, Q, opt);
             if (r.status) FAIL("oracle panic %d", r.status);
