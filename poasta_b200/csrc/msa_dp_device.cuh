@@ -25,7 +25,8 @@
 namespace poasta {
 
 struct DpHdr {
-    uint32_t n_alns, deferred, max_W, failed;
+    uint32_t n_alns, deferred, max_W, failed;  // n_alns: alignments whose rows fit one warp (W <= 1024), slots [0, n_alns)
+    uint32_t n_long, pad0, pad1, pad2;         // alignments of longer queries (cluster kernel), slots [n_fams, n_fams + n_long)
     unsigned long long trace_cursor;  // halves of the trace buffer handed out this sub-round
     unsigned long long pad;
 };
@@ -117,12 +118,15 @@ __global__ void __launch_bounds__(32) dp_prepare_kernel(DpDev D) {
                 out[1] = (uint32_t)F->status;
                 atomicAdd(&D.hdr->failed, 1u);
             } else {
-                const uint32_t a = atomicAdd(&D.hdr->n_alns, 1u);
-                atomicMax(&D.hdr->max_W, W);
+                // queries that fit one warp and longer ones go to different kernels: two slot ranges, graph ids relative to the range
+                const bool is_long = W > (uint32_t)WARP_MAX_W;
+                const uint32_t rel = is_long ? atomicAdd(&D.hdr->n_long, 1u) : atomicAdd(&D.hdr->n_alns, 1u);
+                const uint32_t a = is_long ? D.n_fams + rel : rel;
+                if (is_long) atomicMax(&D.hdr->max_W, W);
                 GraphDesc gd;
                 gd.V = V, gd.node_base = nb, gd.predoff_base = nb + f, gd.max_in_degree = max_deg, gd.n_stored = 0, gd.n_ord_rows = 0, gd.pred_base = pb;
                 AlnDesc ad;
-                ad.graph = a, ad.Q = Q, ad.W = W, ad.query_base = (uint32_t)D.seq_off[gi];
+                ad.graph = rel, ad.Q = Q, ad.W = W, ad.query_base = (uint32_t)D.seq_off[gi];
                 ad.trace_base = 0, ad.ptrace_base = 0;
                 ad.out_base = D.out_base[f], ad.out_cap = V + Q + 2;
                 ad.prow_base = off;
@@ -136,10 +140,10 @@ __global__ void __launch_bounds__(32) dp_prepare_kernel(DpDev D) {
 }
 
 // One warp per alignment (lane 0 works: the update is a chain of dependent list operations).
-__global__ void __launch_bounds__(32) dp_insert_kernel(DpDev D, BatchDev P) {
+__global__ void __launch_bounds__(32) dp_insert_kernel(DpDev D, BatchDev P, uint32_t slot_base) {
     const uint32_t a = blockIdx.x;
     if (a >= P.n_alns || threadIdx.x != 0) return;
-    const uint32_t f = D.aln_family[a];
+    const uint32_t f = D.aln_family[slot_base + a];
     dg::Family *F = D.fams + f;
     dg::Store g(F, D.arena);
     const uint32_t k = F->next_seq, gi = F->seq_first + k;
@@ -234,11 +238,12 @@ static int msa_dp_rounds(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, con
     uint64_t n_workers = std::max<uint64_t>(1, std::min<uint64_t>(nf, (uint64_t)c.n_sms * 16));
     while (n_workers > 1 && n_workers * worker_bytes > ((uint64_t)8 << 30)) n_workers /= 2;
     if (!db.node_base.reserve((size_t)(nf + 1) * 4) || !db.pred_base.reserve((size_t)(nf + 1) * 4) || !db.out_base.reserve((size_t)(nf + 1) * 4) ||
-        !db.gdesc.reserve((size_t)nf * sizeof(GraphDesc)) || !db.adesc.reserve((size_t)nf * sizeof(AlnDesc)) || !db.aln_family.reserve((size_t)nf * 4) ||
+        !db.gdesc.reserve((size_t)2 * nf * sizeof(GraphDesc)) || !db.adesc.reserve((size_t)2 * nf * sizeof(AlnDesc)) ||
+        !db.aln_family.reserve((size_t)2 * nf * 4) ||
         !db.rows.reserve(nb * sizeof(RowRec) + 16) || !db.node_id.reserve(nb * 4 + 16) || !db.node_sym.reserve(nb + 16) ||
         !db.pred_off.reserve((nb + nf + 1) * 4) || !db.pred_rank.reserve(pb * 4 + 16) || !db.workers.reserve(n_workers * worker_bytes) ||
-        !db.hdr.reserve(sizeof(DpHdr)) || !db.counter.reserve(16) || !db.scores.reserve((size_t)nf * 4) || !db.n_pairs.reserve((size_t)nf * 4) ||
-        !db.status.reserve((size_t)nf * 4) || !db.out_r.reserve(ob * 4 + 16) || !db.out_q.reserve(ob * 4 + 16) || !db.scratch.reserve(256) ||
+        !db.hdr.reserve(sizeof(DpHdr)) || !db.counter.reserve(64) || !db.scores.reserve((size_t)2 * nf * 4) || !db.n_pairs.reserve((size_t)2 * nf * 4) ||
+        !db.status.reserve((size_t)2 * nf * 4) || !db.out_r.reserve(ob * 4 + 16) || !db.out_q.reserve(ob * 4 + 16) || !db.scratch.reserve(256) ||
         !db.h_hdr.reserve(sizeof(DpHdr)))
         return POASTA_ERR_CUDA;
     // The trace buffer (M / D rows of every alignment of a round) is sized for graphs of four query lengths per family, bounded by what
@@ -285,7 +290,7 @@ static int msa_dp_rounds(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, con
     D.pred_off = (uint32_t *)db.pred_off.d, D.pred_rank = (uint32_t *)db.pred_rank.d;
     D.workers = (uint8_t *)db.workers.d, D.worker_bytes = worker_bytes, D.wcap = wcap;
     D.hdr = (DpHdr *)db.hdr.d, D.trace_cap = trace_bytes / 2;
-    D.work_counter = (uint32_t *)db.counter.d + 2;
+    D.work_counter = (uint32_t *)db.counter.d + 8;
 
     BatchDev P;
     P.graphs = D.gdesc, P.alns = D.adesc;
@@ -305,6 +310,7 @@ static int msa_dp_rounds(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, con
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&packed_ctas, dp_fill_packed_kernel<true, false>, PK_WARPS * 32, PK_SMEM_BYTES);
     packed_ctas = std::max(1, packed_ctas);
     static const bool timing = getenv("POASTA_TIMING") != nullptr;
+    tl_dp_kernel = 0;
     std::vector<cudaEvent_t> fill_events;  // pairs around every fill launch (the dominant kernel, timed alone for the roofline)
     struct EventGuard {
         std::vector<cudaEvent_t> &v;
@@ -318,23 +324,28 @@ static int msa_dp_rounds(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, con
         D.round = round;
         for (int sub = 0;; ++sub) {
             CK(cudaMemsetAsync(db.hdr.d, 0, sizeof(DpHdr), s));
-            CK(cudaMemsetAsync(db.counter.d, 0, 16, s));  // [0] fill work queue, [1] cluster abort flag, [2] prepare work queue
+            CK(cudaMemsetAsync(db.counter.d, 0, 64, s));  // [0] / [4] fill work queues, [1] / [5] cluster abort flags, [8] prepare work queue
             dp_prepare_kernel<<<(unsigned)n_workers, 32, 0, s>>>(D);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(&h, db.hdr.d, sizeof(DpHdr), cudaMemcpyDeviceToHost, s));
             CK(wait_stream(c));
             ++st.launches;
-            if (h.n_alns) {
-                const uint32_t n = h.n_alns;
-                P.n_alns = n;
-                CK(cudaMemsetAsync(db.scores.d, 0x3F, (size_t)n * 4, s));
+            for (int part = 0; part < 2; ++part) {  // 0: rows that fit one warp, 1: longer queries on the cluster kernel
+                const uint32_t n = part ? h.n_long : h.n_alns, base = part ? nf : 0;
+                if (!n) continue;
+                BatchDev Q = P;
+                Q.graphs = D.gdesc + base, Q.alns = D.adesc + base;
+                Q.scores = P.scores + base, Q.n_pairs = P.n_pairs + base, Q.status = P.status + base;
+                Q.counter = P.counter + 4 * part;  // each launch has its own work queue / abort flag
+                Q.n_alns = n;
+                CK(cudaMemsetAsync(Q.scores, 0x3F, (size_t)n * 4, s));
                 cudaEvent_t f0 = nullptr, f1 = nullptr;
                 CK(cudaEventCreate(&f0));
                 fill_events.push_back(f0);
                 CK(cudaEventCreate(&f1));
                 fill_events.push_back(f1);
                 CK(cudaEventRecord(f0, s));
-                if (h.max_W > (uint32_t)WARP_MAX_W) {
+                if (part) {
                     const uint32_t n_seg_max = (h.max_W + 1023) / 1024;
                     if (n_seg_max > 8) return POASTA_ERR_INTERNAL;  // dp_device_eligible bounds the queries
                     const unsigned cluster_ctas = n_seg_max <= 2 ? 2 : (n_seg_max <= 4 ? 4 : 8);
@@ -347,25 +358,25 @@ static int msa_dp_rounds(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, con
                     int max_clusters = 0;
                     if (cudaOccupancyMaxActiveClusters(&max_clusters, dp_fill_packed_kernel<true, true>, &cfg) != cudaSuccess || max_clusters < 1) max_clusters = 1;
                     cfg.gridDim = dim3((unsigned)std::min<uint64_t>(n, (uint64_t)max_clusters) * cluster_ctas);
-                    CK(cudaLaunchKernelEx(&cfg, dp_fill_packed_kernel<true, true>, P));
-                    tl_dp_kernel = 4;
+                    CK(cudaLaunchKernelEx(&cfg, dp_fill_packed_kernel<true, true>, Q));
+                    tl_dp_kernel = 4;  // sticky for the call: some round needed the cluster kernel
                 } else {
                     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.n_sms * packed_ctas, ((uint64_t)n + PK_WARPS - 1) / PK_WARPS);
-                    dp_fill_packed_kernel<true, false><<<grid, PK_WARPS * 32, PK_SMEM_BYTES, s>>>(P);
-                    tl_dp_kernel = 3;
+                    dp_fill_packed_kernel<true, false><<<grid, PK_WARPS * 32, PK_SMEM_BYTES, s>>>(Q);
+                    if (tl_dp_kernel != 4) tl_dp_kernel = 3;
                 }
                 CK(cudaEventRecord(f1, s));
-                traceback_rows_kernel<<<(n + 3) / 4, 128, 0, s>>>(P);
-                dp_insert_kernel<<<n, 32, 0, s>>>(D, P);
+                traceback_rows_kernel<<<(n + 3) / 4, 128, 0, s>>>(Q);
+                dp_insert_kernel<<<n, 32, 0, s>>>(D, Q, base);
                 CK(cudaGetLastError());
                 st.launches += 3;
             }
             if (timing)
-                fprintf(stderr, "poasta_b200 dp round %u.%d: %u alignments, widest row %u, %u deferred, %u failed, trace %.1f of %.1f GB\n", round, sub,
-                        h.n_alns, h.max_W, h.deferred, h.failed, 2.0 * (double)std::min<unsigned long long>(h.trace_cursor, D.trace_cap) / 1e9,
+                fprintf(stderr, "poasta_b200 dp round %u.%d: %u + %u alignments (one warp / cluster), widest row %u, %u deferred, %u failed, trace %.1f of %.1f GB\n", round, sub,
+                        h.n_alns, h.n_long, h.max_W, h.deferred, h.failed, 2.0 * (double)std::min<unsigned long long>(h.trace_cursor, D.trace_cap) / 1e9,
                         (double)trace_bytes / 1e9);
             if (h.deferred == 0) break;
-            if (h.n_alns == 0) return POASTA_ERR_UNSUPPORTED;  // one alignment's rows do not fit the device
+            if (h.n_alns + h.n_long == 0) return POASTA_ERR_UNSUPPORTED;  // one alignment's rows do not fit the device
         }
     }
     CK(cudaEventRecord(c.ev1, s));

@@ -11,7 +11,7 @@ from poasta_b200 import TIEBREAK_DP, TIEBREAK_EXACT, POAGraph, aligner, msa_batc
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
 mode = TIEBREAK_DP if (len(sys.argv) < 3 or sys.argv[2] == "dp") else TIEBREAK_EXACT
-for rep in range(3):
+for rep in range(int(os.environ.get("PROBE_REPS", "3"))):
     fas = [synth.config2_family(rep * n + f) for f in range(n)]
     t0 = time.perf_counter()
     graphs, scores, cells = msa_batch(fas, tiebreak=mode)
