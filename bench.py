@@ -395,6 +395,7 @@ def main():
             # the same workload through the DP-only mode (optimal scores, co-optimal alignments; not bit-exact at ties)
             torch.cuda.synchronize()
             sub = batches[0][:max(1, len(batches[0]) // 2)]
+            POAGraph.free_many(msa_batch(sub, device=local, tiebreak=TIEBREAK_DP)[0])  # untimed: sizes this mode's buffers
             t0 = time.perf_counter()
             g2, s2, c2 = msa_batch(sub, device=local, tiebreak=TIEBREAK_DP)
             w2 = time.perf_counter() - t0
