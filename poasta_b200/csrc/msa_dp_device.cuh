@@ -179,6 +179,7 @@ static bool dp_device_eligible(const std::vector<EngineFamilyIn> &fams, const po
         if (in.recs->empty()) continue;
         uint64_t qmax = 0, n_seqs = in.recs->size() + in.graph->g.sequences.size();
         for (const auto &r : *in.recs) {
+            if (r.seq.empty()) return false;  // empty queries go through the search kernel (host pipeline)
             qmax = std::max<uint64_t>(qmax, r.seq.size());
             for (unsigned char ch : r.seq)
                 if (!acgt(ch)) return false;

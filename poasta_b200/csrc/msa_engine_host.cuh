@@ -159,7 +159,6 @@ static int msa_engine_run(DeviceContext &c, EngineBuffers &eb, DpBuffers &db, st
             const int rc = msa_dp_rounds(c, eb, db, hf, n_records, seq_bytes, seq_len, prm, st);
             if (rc) return rc;
         }
-        if (prm.tiebreak == 0) db.trace.release();  // the DP-only mode's row store would take the memory the worker slabs are sized for
         // ---- passes: common-case workers first, larger ones for the families that were suspended ----
         std::vector<uint32_t> todo(prm.tiebreak != 0 ? 0 : nf);  // family ids (chunk-local) still to run, with the records they have left
         for (uint32_t i = 0; i < (uint32_t)todo.size(); ++i) todo[i] = i;
