@@ -86,6 +86,17 @@ def test_sub_rounds_when_the_trace_buffer_is_smaller_than_a_round():
         del os.environ["POASTA_DP_TRACE_BYTES"]
 
 
+def test_pipeline_lanes_give_the_same_graphs():
+    """Large batches are split into pipeline lanes (host thread + stream + buffers each); forced here on a small ragged batch."""
+    fas = _ragged(600, 30)
+    for lanes in ("2", "4"):
+        os.environ["POASTA_DP_LANES"] = lanes
+        try:
+            _check(fas)
+        finally:
+            del os.environ["POASTA_DP_LANES"]
+
+
 def test_existing_graphs_continue_on_the_device():
     fas = _ragged(700, 10, lo=6, hi=8)
     first, rest, expect = [], [], []
