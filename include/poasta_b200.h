@@ -108,6 +108,9 @@ int poasta_last_dp_kernel(void);
  * persistent kernel, everything on the device), 2 the device-resident DP-only rounds (tiebreak = 1: pack, fill, traceback and graph
  * update on the device), 3 the per-round host pipeline of the DP-only mode (inputs the packed kernels do not cover, ends-free). */
 int poasta_last_msa_path(void);
+/* Visited-table layout of the last search launch of poasta_align_batch on this thread (diagnostic): 0 none yet, 1 dense V x W,
+ * 2 blocked (64-offset blocks handed out on first touch; picked when the dense table of one alignment would pass 64 MB). */
+int poasta_last_search_table(void);
 /* Device-resident DP-only rounds of the last poasta_msa_batch* on this thread: milliseconds of the dp_fill_packed_kernel launches
  * alone (CUDA events around each launch) and their number - the dominant kernel of that pipeline, for roofline figures. */
 int poasta_last_batch_fill_ms(double *fill_ms, uint32_t *n_fill_launches);

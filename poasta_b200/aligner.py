@@ -126,6 +126,11 @@ def last_msa_path():
     return int(_lib.load().poasta_last_msa_path())
 
 
+def last_search_table():
+    """Visited-table layout of the last search launch of align_batch: 1 dense, 2 blocked (diagnostic)."""
+    return int(_lib.load().poasta_last_search_table())
+
+
 def last_batch_fill_ms():
     """(milliseconds, launches) of the DP fill kernel alone in the last device-resident DP-only build."""
     ms, n = C.c_double(), C.c_uint32()

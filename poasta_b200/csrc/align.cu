@@ -485,6 +485,7 @@ static thread_local double tl_lane_max_ms = -1;  // msa batches: the largest per
 static thread_local uint32_t tl_launches = 0;
 static thread_local int tl_dp_kernel = 0;  // poasta_last_dp_kernel
 static thread_local int tl_msa_path = 0;   // poasta_last_msa_path
+static thread_local int tl_search_table = 0;  // poasta_last_search_table: 1 dense, 2 blocked (last search launch of poasta_align_batch)
 static thread_local double tl_fill_ms = 0;  // poasta_last_batch_fill_ms
 static thread_local uint32_t tl_fill_launches = 0;
 static thread_local uint64_t tl_cells = 0;
@@ -828,25 +829,38 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     const uint64_t worst = ((uint64_t)pr.max_V + pr.max_Q + 4) * std::max<uint64_t>(prm.mismatch, (uint64_t)prm.gap_open + prm.gap_extend) +
                            prm.gap_open;
     const bool cell16 = worst < replay::CELL16_LIMIT;
-    const uint64_t plane_bytes = up(4 * cells_per_aln * (cell16 ? 2 : 4));  // records {M, D, I, epoch}
+    const uint64_t rec_bytes = cell16 ? 8 : 16;  // records {M, D, I, epoch}
+    // Blocked visited table (replay_core.hpp BLK_SHIFT) when a dense V x W table would be large: reads against a big fixed graph
+    // touch a sliver of it (config 5: 400 MB dense per worker = 245 workers per GPU; blocked: ~50 MB = every warp slot busy).
+    // The pool holds one block per node (ends-free alignments start a state at offset 0 of every node) plus room for the search;
+    // an alignment that outgrows it is rerun with the dense table (full_arenas).
+    const int blocked_knob = getenv("POASTA_BLOCKED_TABLE") ? atoi(getenv("POASTA_BLOCKED_TABLE")) : -1;  // tests: 1 forces, 0 forbids
+    const uint32_t bpr = (dmax.W + replay::BLK_CELLS - 1) / replay::BLK_CELLS;
+    const uint64_t dense_blocks = (uint64_t)pr.max_V * bpr;
+    uint64_t max_blocks = std::min<uint64_t>(replay::BMAP_BLOCK_MASK, (uint64_t)pr.max_V + std::max<uint64_t>(16384, dense_blocks / 32));
+    if (const char *e = getenv("POASTA_BLOCKED_POOL_BLOCKS")) max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, strtoull(e, nullptr, 10)));  // tests: forces the dense rerun
+    const bool blocked = !full_arenas && (blocked_knob == 1 || (blocked_knob != 0 && cells_per_aln * rec_bytes > ((uint64_t)64 << 20) &&
+                                                                 max_blocks * 2 < dense_blocks));
+    const uint64_t plane_bytes = blocked ? up(max_blocks * replay::BLK_CELLS * rec_bytes) : up(cells_per_aln * rec_bytes);
     // the live queue is a small fraction of the table: size the item arena for that and retry the rare overflow at full size
     // measured high-water mark of the live queue: <= 1 % of the cells (16k items at V = 1770, Q = 1000)
     // (the inadmissible path heuristic on divergent input re-queues states: high-water 0.99 x cells seen in tools/fuzz_core_vs_oracle.py)
-    uint64_t max_items = full_arenas ? 262144 + 2 * cells_per_aln : 32768 + cells_per_aln / 32;
+    uint64_t max_items = full_arenas ? 262144 + 2 * cells_per_aln : 32768 + cells_per_aln / (blocked ? 128 : 32);
     max_items = (max_items + 7) & ~(uint64_t)7;  // whole chunks (replay_core.hpp CHUNK)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // in reference-exact mode the DP pass keeps no trace store, so most of HBM can hold search slabs
     static const double slab_fraction = getenv("POASTA_SLAB_FRACTION") ? atof(getenv("POASTA_SLAB_FRACTION")) : 0.6;
     const uint64_t budget = std::max<uint64_t>((uint64_t)2 << 30, (uint64_t)(slab_fraction * (double)total_b)) / tl_lane_count;
-    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_bits = 0, off_dfa = 0;
+    uint64_t slab = 0, off_qhead = 0, off_items = 0, off_free = 0, off_reached = 0, off_bits = 0, off_dfa = 0, off_bmap = 0;
     off_qhead = SLAB_CELLS + plane_bytes;
     off_items = off_qhead + up((uint64_t)dmax.f_max * 12);
     off_free = off_items + up(max_items * 16);
     off_reached = off_free + up(max_items * 4);                   // reached bounds: 2 words per node
     off_bits = off_reached + up((uint64_t)pr.max_V * 8);          // reached-offset bitmap: Wb words per node
     off_dfa = off_bits + up((uint64_t)pr.max_V * ((dmax.W + 31) / 32) * 4);
-    slab = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);           // DFA frames: 6 words
+    off_bmap = off_dfa + up((uint64_t)(pr.max_V + 2) * 24);       // DFA frames: 6 words
+    slab = off_bmap + (blocked ? up(dense_blocks * 4) : 0);      // block map of the blocked table
     const uint64_t want_workers = std::min<uint64_t>(n, (uint64_t)c.n_sms * 32);  // 32 CTAs of one warp per SM
     uint64_t workers = std::max<uint64_t>(1, std::min<uint64_t>(want_workers, budget / slab));
     const unsigned warps_per_cta = 1;  // one warp per CTA (replay_kernel.cuh)
@@ -856,7 +870,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         if (!c.r_slabs.reserve(workers * slab)) return POASTA_ERR_CUDA;
     }
     {
-        const uint64_t sig = slab * 1000003ull + off_qhead * 10007ull + off_items * 101ull + off_dfa + (cell16 ? 1ull << 62 : 0);
+        const uint64_t sig = slab * 1000003ull + off_qhead * 10007ull + off_items * 101ull + off_dfa + (cell16 ? 1ull << 62 : 0) +
+                             (blocked ? (1ull << 61) + bpr * 7919ull + max_blocks * 31ull : 0);
         if (c.slab_ptr != c.r_slabs.d || c.slab_sig != sig) c.slab_ptr = c.r_slabs.d, c.slab_sig = sig, c.slab_zeroed_bytes = 0;
         if (workers * slab > c.slab_zeroed_bytes) {
             CK(cudaMemsetAsync((uint8_t *)c.r_slabs.d + c.slab_zeroed_bytes, 0, workers * slab - c.slab_zeroed_bytes, c.stream));
@@ -903,6 +918,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
     B.slab_bytes = slab;
     B.off_qhead = off_qhead, B.off_items = off_items, B.off_free = off_free, B.off_rb = off_reached, B.off_bits = off_bits, B.off_dfa = off_dfa;
     B.max_items = (uint32_t)max_items;
+    B.off_bmap = off_bmap, B.bpr = bpr, B.max_blocks = (uint32_t)max_blocks;
+    tl_search_table = blocked ? 2 : 1;
     B.counter = (uint32_t *)c.counter.d;
     B.scores = (uint32_t *)c.scores.d;
     B.n_pairs = (uint32_t *)c.n_pairs.d;
@@ -922,7 +939,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         auto launch = [&](auto cell, auto heur) {
             using CellT = decltype(cell);
             constexpr int H = decltype(heur)::value;
-            replay_kernel<CellT, 32, H><<<grid, block, 0, s>>>(B);
+            if (blocked) replay_kernel<CellT, 32, H, true><<<grid, block, 0, s>>>(B);
+            else replay_kernel<CellT, 32, H, false><<<grid, block, 0, s>>>(B);
         };
         auto launch_cell = [&](auto cell) {
             if (prm.heuristic == 0) launch(cell, std::integral_constant<int, 0>{});
@@ -973,8 +991,8 @@ static int run_replay(DeviceContext &c, const PackedReplay &pr, const poasta_par
         const uint32_t *st = (const uint32_t *)c.h_stats.h;
         uint64_t sum = 0, mx = 0;
         for (size_t i = 0; i < n; ++i) sum += st[4 * i + 1], mx = std::max<uint64_t>(mx, st[4 * i + 1]);
-        fprintf(stderr, "poasta_b200 lane %d: search launch of %zu alignments, %u workers, %.1f ms; visited states mean %.0f max %llu\n", tl_lane,
-                (size_t)n, (unsigned)workers, ms, (double)sum / (double)n, (unsigned long long)mx);
+        fprintf(stderr, "poasta_b200 lane %d: search launch of %zu alignments, %u workers x %.1f MB (%s table), %.1f ms; visited states mean %.0f max %llu\n",
+                tl_lane, (size_t)n, (unsigned)workers, slab / 1048576.0, blocked ? "blocked" : "dense", ms, (double)sum / (double)n, (unsigned long long)mx);
     }
     return 0;
 }
@@ -1272,6 +1290,7 @@ int poasta_last_batch_search_counts(uint64_t *num_queued, uint64_t *num_visited,
 
 int poasta_last_dp_kernel(void) { return tl_dp_kernel; }
 int poasta_last_msa_path(void) { return tl_msa_path; }
+int poasta_last_search_table(void) { return tl_search_table; }
 int poasta_last_batch_fill_ms(double *fill_ms, uint32_t *n_fill_launches) {
     if (fill_ms) *fill_ms = tl_fill_ms;
     if (n_fill_launches) *n_fill_launches = tl_fill_launches;

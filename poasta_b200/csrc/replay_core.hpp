@@ -94,6 +94,14 @@ template <typename CellT> struct alignas(4 * sizeof(CellT)) Rec {
 #endif
 constexpr uint32_t QWIN = RP_QWIN;  // priorities whose stack heads are kept in the fast window (power of two)
 
+// BLOCKED visited table (reads against a large fixed graph, SURVEY 8d config 5: V x W = 25,000 x 2,000 records = 400 MB dense, of
+// which one 2 kb read touches a sliver): records live in BLOCKS of 64 consecutive offsets of one node, handed out from a pool on
+// first touch; a map entry per (node, offset / 64) holds (map epoch << 20 | block number). The reference's table is blocked for the
+// same reason (gap_affine.rs:442-548). Entries of another map epoch read as "no block", so the map is never reset between
+// alignments either; the records inside a recycled block carry their own (older) alignment epochs and read as unvisited.
+constexpr uint32_t BLK_SHIFT = 6, BLK_CELLS = 1u << BLK_SHIFT;
+constexpr uint32_t BMAP_EPOCH_MAX = 0xFFFu, BMAP_BLOCK_MASK = 0xFFFFFu;
+
 struct alignas(16) NodeA {
     uint32_t succ_off, bub_off;  // into Graph::succ / Graph::bub (quadruples)
     uint32_t counts;             // n_succ | n_bub << 16
@@ -142,7 +150,24 @@ struct Scratch {  // one slab per in-flight alignment
     uint32_t Wb;           // words per bitmap row = (W + 31) / 32
     uint32_t *dfa;         // (V + 2) frames of 6 words: node, offset, next successor slot, end slot, dist_min, dist_max
     uint32_t W, max_items, f_max;
+    // blocked visited table only (Search<..., BLOCKED = true>): planes = the block pool
+    uint32_t *bmap = nullptr;  // V * bpr entries
+    uint32_t bpr = 0;          // map entries per node = ceil(W / 64)
+    uint32_t max_blocks = 0;   // pool capacity (< 2^20)
+    uint32_t bmap_epoch = 0;   // 1 .. BMAP_EPOCH_MAX
 };
+
+// Read-only lookup of the record of (node, off); nullptr = no block there (blocked table only).
+template <typename CellT, bool BLOCKED>
+RP_HD const Rec<CellT> *table_lookup(const void *planes, const uint32_t *bmap, uint32_t bpr, uint32_t bmap_epoch, uint32_t W, uint32_t node, uint32_t off) {
+    if constexpr (!BLOCKED) {
+        return static_cast<const Rec<CellT> *>(planes) + (size_t)node * W + off;
+    } else {
+        const uint32_t e = bmap[(size_t)node * bpr + (off >> BLK_SHIFT)];
+        if ((e >> 20) != bmap_epoch) return nullptr;
+        return static_cast<const Rec<CellT> *>(planes) + ((size_t)(e & BMAP_BLOCK_MASK) << BLK_SHIFT) + (off & (BLK_CELLS - 1));
+    }
+}
 
 struct Params {
     uint32_t x, o, e;
@@ -187,17 +212,22 @@ RP_HD uint32_t rp_ctz(uint32_t x) {
 
 // ---- prune test (bubbles/reached.rs:38-255 + gap_affine.rs:780-792) -----------------------------------------------
 // Returns 0 = can still improve (keep), 1 = prune, 2 = score arithmetic wrapped (the reference would panic).
-template <typename CellT>
-struct PruneCtx {
-    const Rec<CellT> *table;  // the visited table; record of (node, off) at node * W + off
+template <bool BLOCKED> struct PruneBlocks {};  // the block map of the blocked table; nothing for the dense one
+template <> struct PruneBlocks<true> {
+    const uint32_t *bmap;
+    uint32_t bpr, bmap_epoch;
+};
+template <typename CellT, bool BLOCKED>
+struct PruneCtx : PruneBlocks<BLOCKED> {
+    const Rec<CellT> *table;  // the visited table; record of (node, off) at node * W + off (blocked table: the block pool)
     const uint32_t *rb;       // reached bounds per node
     const uint32_t *rbits;    // reached-offset bitmap, Wb words per node
     uint32_t W, Wb, Q, o, e;
 };
 
 // can_improve_bubble for one bubble; true = the state can still improve on it (no prune from this bubble)
-template <typename CellT>
-RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, uint32_t off, uint32_t st, uint32_t score,
+template <typename CellT, bool BLOCKED>
+RP_HD bool prune_bubble(const PruneCtx<CellT, BLOCKED> &c, const BubQ &b, uint32_t node, uint32_t off, uint32_t st, uint32_t score,
                         bool &wrapped) {
     constexpr CellT CUNV = CellTraits<CellT>::CUNV;
     RP_CNT(C_PRUNE_BUB);
@@ -209,7 +239,8 @@ RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, 
     }
     auto gap = [&](uint32_t len) -> uint32_t { return len == 0 ? 0u : c.o + len * c.e; };  // gap_cost(Match, len)
     const uint32_t tmin = off + b.min_d, tmax = off + b.max_d;
-    const Rec<CellT> *mrow = c.table + (size_t)b.exit * c.W;
+    const Rec<CellT> *mrow = c.table + (size_t)b.exit * c.W;  // dense table only
+    (void)mrow;
     const uint32_t *bits = c.rbits + (size_t)b.exit * c.Wb;
     // reached offsets = set bits of the exit's bitmap row, all inside [lo, hi1): a range query is one or two word operations
     // (round 1 scanned the Match cells one by one: ~10 dependent probes per visited state)
@@ -240,7 +271,14 @@ RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, 
         }
     };
     auto S = [&](uint32_t r, uint32_t plus) -> uint32_t {  // get_score(exit, r, Match) + plus, with the NonMax checks
-        const CellT v = mrow[r].m;  // a reached offset was written by THIS alignment: no epoch test
+        // a reached offset was written by THIS alignment: no epoch test (and its block exists)
+        CellT v;
+        if constexpr (!BLOCKED) {
+            v = mrow[r].m;
+        } else {
+            const Rec<CellT> *rec = table_lookup<CellT, true>(c.table, c.bmap, c.bpr, c.bmap_epoch, c.W, b.exit, r);
+            v = rec ? rec->m : CUNV;
+        }
         RP_CNT(C_PRUNE_SCORE);
         const uint32_t t = (uint32_t)v + plus;
         if (CellTraits<CellT>::CHECK_WRAP && (v == CUNV || t == UNV)) wrapped = true;
@@ -289,12 +327,12 @@ RP_HD bool prune_bubble(const PruneCtx<CellT> &c, const BubQ &b, uint32_t node, 
 }
 
 // All bubbles of a node, innermost first (index.rs order); one 128-bit load per quadruple.
-template <typename CellT>
-RP_HD int prune_eval(const PruneCtx<CellT> &c, const BubQ *bubs, uint32_t n_bub, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
+template <typename CellT, bool BLOCKED>
+RP_HD int prune_eval(const PruneCtx<CellT, BLOCKED> &c, const BubQ *bubs, uint32_t n_bub, uint32_t node, uint32_t off, uint32_t st, uint32_t score) {
     bool wrapped = false;
     for (uint32_t k = 0; k < n_bub; ++k) {
         const BubQ b = bubs[k];
-        const bool can = prune_bubble<CellT>(c, b, node, off, st, score, wrapped);
+        const bool can = prune_bubble<CellT, BLOCKED>(c, b, node, off, st, score, wrapped);
         if (wrapped) return 2;
         if (!can) return 1;  // !all(can_improve)
     }
@@ -305,7 +343,8 @@ RP_HD int prune_eval(const PruneCtx<CellT> &c, const BubQ *bubs, uint32_t n_bub,
 // possible score (every node deleted + every query base inserted) is below CELL16_LIMIT.
 // HEUR = Params::heuristic as a compile-time constant: every push evaluates h(), and the three heuristics inlined at every
 // push site tripled the kernel's code size (instruction-cache misses were 20-30 % of its stall cycles).
-template <typename CellT, int HEUR>
+// BLOCKED = the visited table is a pool of 64-offset blocks behind a map (see BLK_SHIFT); false = dense V x W (the default).
+template <typename CellT, int HEUR, bool BLOCKED = false>
 struct Search {
     static constexpr CellT CUNV = CellTraits<CellT>::CUNV;
     static constexpr bool CHECK_WRAP = CellTraits<CellT>::CHECK_WRAP;
@@ -317,6 +356,7 @@ struct Search {
     uint32_t n_items = 0, n_free = 0;  // bump pointer into the item arena (slots, multiple of CHUNK); height of the recycled-chunk stack
     uint32_t f_cur = 0, f_hi = 0, win_base = 0;
     uint32_t f_top = 0;  // highest priority queued so far: the next alignment of this worker clears qhead[0 .. f_top]
+    uint32_t n_blocks = 0;  // blocked table: blocks handed out so far
     bool q_empty = true;
     int err = RP_OK;
     // counting builds: how predictable is the next pop? (the item below the popped one / an item queued since / anything else)
@@ -334,7 +374,26 @@ struct Search {
 
     // ---- visited table -------------------------------------------------------------------------
     using R = Rec<CellT>;
-    RP_HD R *rec_ptr(uint32_t node, uint32_t off) const { return static_cast<R *>(s.planes) + (size_t)node * s.W + off; }
+    // the record of (node, off); the blocked table hands out the block on first touch (reads included: every read of the search
+    // loop is of a record it wrote earlier or writes next)
+    RP_HD R *rec_ptr(uint32_t node, uint32_t off) {
+        if constexpr (!BLOCKED) {
+            return static_cast<R *>(s.planes) + (size_t)node * s.W + off;
+        } else {
+            uint32_t *me = s.bmap + (size_t)node * s.bpr + (off >> BLK_SHIFT);
+            uint32_t e = *me;
+            if ((e >> 20) != s.bmap_epoch) {
+                if (n_blocks >= s.max_blocks) {
+                    err = RP_OUT_OF_BLOCKS;  // the caller reruns the alignment with a dense table; block 0 is valid memory until the loop stops
+                    e = 0;
+                } else {
+                    e = n_blocks++;
+                    *me = (s.bmap_epoch << 20) | e;
+                }
+            }
+            return static_cast<R *>(s.planes) + ((size_t)(e & BMAP_BLOCK_MASK) << BLK_SHIFT) + (off & (BLK_CELLS - 1));
+        }
+    }
     // one vector load; a record of another epoch reads as three unvisited cells (stamped with the current epoch, so that
     // storing it back after changing one cell makes the whole record current)
     RP_HD R load(const R *ptr) const {
@@ -348,8 +407,15 @@ struct Search {
         else if (st == ST_D) r.d = v;
         else r.i = v;
     }
-    RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {
-        const CellT v = field(load(rec_ptr(node, off)), st);
+    RP_HD uint32_t get(uint32_t node, uint32_t off, uint32_t st) const {  // read-only (the backtrace): never hands out a block
+        const R *ptr;
+        if constexpr (!BLOCKED) {
+            ptr = static_cast<const R *>(s.planes) + (size_t)node * s.W + off;
+        } else {
+            ptr = table_lookup<CellT, true>(s.planes, s.bmap, s.bpr, s.bmap_epoch, s.W, node, off);
+            if (!ptr) return UNV;
+        }
+        const CellT v = field(load(ptr), st);
         return v == CUNV ? UNV : (uint32_t)v;
     }
     RP_HD void set(uint32_t node, uint32_t off, uint32_t st, uint32_t v) {
@@ -475,6 +541,45 @@ struct Search {
         }
         RP_ACC(prof_push);
     }
+    // push() with the priority computed earlier (prepare_initial)
+    RP_HD void push_f(uint32_t node, uint32_t off, uint32_t st, uint32_t score, uint32_t f) {
+        RP_T0;
+        RP_CNT(C_PUSH);
+        RP_STAT(++stat_pushes;)
+        if (f >= s.f_max) {
+            err = RP_PRIORITY_RANGE;
+            return;
+        }
+        if (f > f_top) f_top = f;
+        uint32_t *head = head_ptr(f) + st;
+        const uint32_t hv = *head;
+        uint32_t slot, aux = 0;
+        if (hv == 0 || (hv & (CHUNK - 1)) == 0) {  // empty stack, or its top chunk is full: open a chunk
+            if (n_free) {
+                slot = s.free_slots[--n_free] * CHUNK;
+            } else {
+                if (n_items + CHUNK > s.max_items) {
+                    err = RP_OUT_OF_ITEMS;
+                    return;
+                }
+                slot = n_items;
+                n_items += CHUNK;
+            }
+            aux = hv;
+        } else {
+            slot = hv;  // the slot above the current top (top = hv - 1)
+        }
+        s.items[slot] = Item{score, node, off, aux};
+        *head = slot + 1;
+        if (q_empty) {
+            f_cur = f_hi = f;
+            q_empty = false;
+        } else {
+            if (f < f_cur) f_cur = f;
+            if (f > f_hi) f_hi = f;
+        }
+        RP_ACC(prof_push);
+    }
     RP_HD bool pop(Item &out, uint32_t &st) {
         if (q_empty) return false;
         for (;;) {
@@ -528,8 +633,10 @@ struct Search {
         if (nb == 0) return false;
         RP_T0;
         RP_CNT(C_PRUNE_CALL);
-        const PruneCtx<CellT> c{static_cast<const R *>(s.planes), s.rb, s.rbits, s.W, s.Wb, Q, p.o, p.e};
-        const int r = prune_eval<CellT>(c, g.bub + a.bub_off, nb, node, off, st, score);
+        PruneCtx<CellT, BLOCKED> c;
+        c.table = static_cast<const R *>(s.planes), c.rb = s.rb, c.rbits = s.rbits, c.W = s.W, c.Wb = s.Wb, c.Q = Q, c.o = p.o, c.e = p.e;
+        if constexpr (BLOCKED) c.bmap = s.bmap, c.bpr = s.bpr, c.bmap_epoch = s.bmap_epoch;
+        const int r = prune_eval<CellT, BLOCKED>(c, g.bub + a.bub_off, nb, node, off, st, score);
         if (r == 2) err = RP_SCORE_WRAP;
         RP_ACC(prof_prune);
 #if defined(RP_PROFILE)
@@ -588,7 +695,38 @@ struct Search {
         return false;
     }
 
-    // The whole alignment (astar.rs:108-226 + mod.rs:114-145 non-empty graph).
+    // Ends-free alignments start one state at offset 0 of EVERY node. The per-node part of that - the heuristic value, the visited
+    // record, (blocked table) the node's first block - is independent work, so all lanes of the worker share it here; lane 0 then
+    // queues the states in the reference's order (run<true>). Priorities are parked in the DFA frame array, which is unused until
+    // the first extension. Returns false when the shortcut does not apply (the caller then uses run<false>). Warp-uniform result.
+    RP_HD bool prepare_initial(uint32_t lane, uint32_t n_lanes) {
+        if (p.mode == 0) return false;
+        if (BLOCKED && s.max_blocks < g.V) return false;
+        uint32_t *ftmp = s.dfa;
+        for (uint32_t n = lane; n < g.V; n += n_lanes) {
+            if (n == g.start || n == g.end) {
+                ftmp[n] = UNV;
+                continue;
+            }
+            const NodeB b = node_b(n);
+            ftmp[n] = h(n, b.dist_min, b.dist_max, 0, ST_M);  // score 0
+            R *ptr;
+            if constexpr (BLOCKED) {  // block n belongs to offsets [0, 64) of node n
+                s.bmap[(size_t)n * s.bpr] = (s.bmap_epoch << 20) | n;
+                ptr = static_cast<R *>(s.planes) + ((size_t)n << BLK_SHIFT);
+            } else {
+                ptr = static_cast<R *>(s.planes) + (size_t)n * s.W;
+            }
+            R r = load(ptr);  // set(n, 0, ST_M, 0)
+            r.m = 0;
+            *ptr = r;
+        }
+        if (BLOCKED) n_blocks = g.V;
+        return true;
+    }
+
+    // The whole alignment (astar.rs:108-226 + mod.rs:114-145 non-empty graph). PREPARED: prepare_initial() has run.
+    template <bool PREPARED = false>
     RP_HD Result run(uint32_t *out_r, uint32_t *out_q, uint32_t cap) {
         Result res{0, 0, RP_OK, 0, 0, 0};
         const uint32_t oe8 = (p.o + p.e) & 0xFF;  // the queued delta is a u8 sum in the reference (gap_affine.rs:288)
@@ -604,7 +742,12 @@ struct Search {
             bool any = false;
             for (uint32_t n = g.V; n-- > 0;)
                 if (n != g.start && n != g.end) {
-                    push_initial(n);
+                    if constexpr (PREPARED) {
+                        push_f(n, 0, ST_M, 0, s.dfa[n]);
+                        ++res.num_queued;
+                    } else {
+                        push_initial(n);
+                    }
                     any = true;
                 }
             if (!any) push_initial(g.start);

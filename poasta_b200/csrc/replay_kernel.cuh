@@ -30,6 +30,9 @@ struct ReplayDev {
     uint8_t *slabs;
     uint64_t slab_bytes, off_qhead, off_items, off_free, off_rb, off_bits, off_dfa;  // byte offsets inside a slab (header at 0, records at SLAB_CELLS)
     uint32_t max_items;
+    // blocked visited table (replay_core.hpp BLK_SHIFT): the records area [SLAB_CELLS, off_qhead) is the block pool
+    uint64_t off_bmap;
+    uint32_t bpr, max_blocks;
     uint32_t *counter, *scores, *n_pairs, *out_r, *out_q;
     int32_t *status;
     uint32_t *stats;  // per alignment: queued, visited, pruned, item high-water mark
@@ -45,9 +48,24 @@ constexpr int REPLAY_MAX_WARPS_PER_CTA = 1;
 // host when it is (re)allocated or its layout changes, so epoch 0 means "never written".
 constexpr uint64_t SLAB_CELLS = 256;
 struct SlabHeader {
-    uint32_t epoch;    // epoch of the last alignment this worker ran
-    uint32_t dirty_f;  // priorities [0, dirty_f) of qhead may be non-zero
+    uint32_t epoch;      // epoch of the last alignment this worker ran
+    uint32_t dirty_f;    // priorities [0, dirty_f) of qhead may be non-zero
+    uint32_t map_epoch;  // blocked table: epoch of the block map entries the last alignment wrote (0 = none yet)
 };
+// Start of an alignment on a worker with a blocked visited table: next map epoch; the map is zeroed only when the 12-bit epoch wraps.
+__device__ __forceinline__ uint32_t worker_begin_blocks(uint8_t *slab, uint64_t off_bmap, uint64_t map_entries, uint32_t lane) {
+    SlabHeader *hdr = reinterpret_cast<SlabHeader *>(slab);
+    uint32_t mep = hdr->map_epoch + 1;
+    if (mep > replay::BMAP_EPOCH_MAX) {
+        uint32_t *m = reinterpret_cast<uint32_t *>(slab + off_bmap);
+        for (uint64_t i = lane; i < map_entries; i += 32) m[i] = 0;
+        mep = 1;
+    }
+    __syncwarp();
+    if (lane == 0) hdr->map_epoch = mep;
+    __syncwarp();
+    return mep;
+}
 template <typename CellT> struct EpochTraits;
 template <> struct EpochTraits<uint16_t> { static constexpr uint32_t MAX = 0xFFFEu; };
 template <> struct EpochTraits<uint32_t> { static constexpr uint32_t MAX = 0xFFFFFFFEu; };
@@ -87,7 +105,7 @@ __device__ __forceinline__ void worker_end_alignment(uint8_t *slab, uint32_t epo
 
 // MINB = minimum resident CTAs per SM the register allocation must allow. Only lane 0 of a warp runs the state machine
 // but registers are allocated for all 32 lanes, so the register count decides how many alignments are in flight per SM.
-template <typename CellT, int MINB, int HEUR>
+template <typename CellT, int MINB, int HEUR, bool BLOCKED = false>
 __global__ void __launch_bounds__(32, MINB) replay_kernel(ReplayDev B) {
     __shared__ uint32_t s_qwin[replay::QWIN * 3];  // queue-head window of the worker
     __shared__ replay::Scratch s_scr;              // the worker's pointer blocks at fixed shared-memory addresses
@@ -104,6 +122,8 @@ __global__ void __launch_bounds__(32, MINB) replay_kernel(ReplayDev B) {
         const replay::ScratchDims dims(gd.V, ad.Q, B.prm.x, B.prm.o, B.prm.e);
         const uint32_t Wb = (dims.W + 31) / 32;
         const uint32_t epoch = worker_begin_alignment<CellT>(slab, B.off_qhead - SLAB_CELLS, B.off_qhead, B.off_rb, B.off_bits, gd.V, Wb, s_qwin, lane);
+        uint32_t map_epoch = 0;
+        if (BLOCKED) map_epoch = worker_begin_blocks(slab, B.off_bmap, (uint64_t)gd.V * B.bpr, lane);
         if (lane == 0) {
             replay::Graph &g = s_gr;
             g.V = gd.V, g.start = gd.start, g.end = gd.end;
@@ -126,8 +146,17 @@ __global__ void __launch_bounds__(32, MINB) replay_kernel(ReplayDev B) {
             s.dfa = reinterpret_cast<uint32_t *>(slab + B.off_dfa);
             s.W = dims.W, s.f_max = dims.f_max;
             s.max_items = B.max_items;
-            replay::Search<CellT, HEUR> search(g, B.queries + ad.query_base, ad.Q, B.prm, s);
-            const replay::Result r = search.run(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
+            s.bmap = reinterpret_cast<uint32_t *>(slab + B.off_bmap), s.bpr = B.bpr, s.max_blocks = B.max_blocks, s.bmap_epoch = map_epoch;
+        }
+        __syncwarp();
+        // every lane holds a view of the search (references into shared memory): the lanes share the per-node start-up work of an
+        // ends-free alignment, then lane 0 runs the state machine
+        replay::Search<CellT, HEUR, BLOCKED> search(s_gr, B.queries + ad.query_base, ad.Q, B.prm, s_scr);
+        const bool prepared = search.prepare_initial(lane, 32u);
+        __syncwarp();
+        if (lane == 0) {
+            const replay::Result r = prepared ? search.template run<true>(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap)
+                                              : search.template run<false>(B.out_r + ad.out_base, B.out_q + ad.out_base, ad.out_cap);
             worker_end_alignment(slab, epoch, search.f_top);
             B.scores[a] = r.score;
             B.n_pairs[a] = r.status == replay::RP_OK ? r.n_pairs : 0;

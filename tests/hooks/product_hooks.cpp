@@ -280,15 +280,44 @@ int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_
     const uint32_t Wb = (d.W + 31) / 32;
     std::vector<uint32_t> rbits((size_t)view->n_nodes * Wb, 0);
     Scratch s{planes.data(), epoch, qhead.data(), qwin.data(), items.data(), free_slots.data(), rb.data(), rbits.data(), Wb, dfa.data(), d.W, max_items, d.f_max};
+    // RP_HOST_BLOCKED=<pool blocks>: the blocked visited table (64-offset blocks behind a map) instead of the dense one; the map is
+    // pre-filled with entries of OTHER map epochs, which must read as "no block"
+    const bool blocked = getenv("RP_HOST_BLOCKED") != nullptr;
+    std::vector<uint32_t> bmap;
+    if (blocked) {
+        s.bpr = (d.W + rp::BLK_CELLS - 1) / rp::BLK_CELLS;
+        s.max_blocks = (uint32_t)std::min<uint64_t>((uint64_t)atoll(getenv("RP_HOST_BLOCKED")), rp::BMAP_BLOCK_MASK);
+        planes.resize(std::max<size_t>(planes.size(), (size_t)s.max_blocks * rp::BLK_CELLS * (cell16 ? 8 : 16)), 0);
+        s.planes = planes.data();
+        s.bmap_epoch = 5;
+        bmap.resize((size_t)view->n_nodes * s.bpr);
+        uint32_t x = 999;
+        for (auto &e : bmap) {
+            x = x * 1664525u + 1013904223u;
+            uint32_t other = (x >> 8) % rp::BMAP_EPOCH_MAX + 1;
+            if (other == s.bmap_epoch) other = 6;
+            e = (other << 20) | ((x >> 3) & rp::BMAP_BLOCK_MASK);
+        }
+        s.bmap = bmap.data();
+    }
     Params p{(uint32_t)x, (uint32_t)o, (uint32_t)e, mode, heuristic};
     const uint32_t ocap = view->n_nodes + qlen + 2;
     std::vector<uint32_t> out_r(ocap), out_q(ocap);
     Result r;
     uint32_t used_blocks = 0, used_items = 0;
     auto go = [&](auto cell, auto heur) {
-        rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
-        r = search.run(out_r.data(), out_q.data(), ocap);
-        used_items = search.n_items;
+        // RP_HOST_PREINIT: the start-up of an ends-free alignment through prepare_initial + run<true> (what the device's lanes share)
+        const bool preinit = getenv("RP_HOST_PREINIT") != nullptr;
+        if (blocked) {
+            rp::Search<decltype(cell), decltype(heur)::value, true> search(g, seq, qlen, p, s);
+            r = (preinit && search.prepare_initial(0, 1)) ? search.template run<true>(out_r.data(), out_q.data(), ocap) : search.run(out_r.data(), out_q.data(), ocap);
+            used_items = search.n_items;
+            used_blocks = search.n_blocks;
+        } else {
+            rp::Search<decltype(cell), decltype(heur)::value> search(g, seq, qlen, p, s);
+            r = (preinit && search.prepare_initial(0, 1)) ? search.template run<true>(out_r.data(), out_q.data(), ocap) : search.run(out_r.data(), out_q.data(), ocap);
+            used_items = search.n_items;
+        }
     };
     auto go_cell = [&](auto cell) {
         if (heuristic == 0) go(cell, std::integral_constant<int, 0>{});

@@ -44,3 +44,43 @@ def test_config5_reads_against_fixed_graph():
     for q, r in zip(reads[:4], res):
         st, sc, pairs, _ = H.oracle_align(g, q)
         assert st == 0 and r.score == sc and r.alignment == pairs
+
+
+def test_blocked_visited_table_matches_the_dense_one_and_the_oracle():
+    """The search's visited table as 64-offset blocks handed out on first touch (picked for large V x W; forced here on a small
+    graph): alignments and A* counters equal the oracle's in ends-free and global mode, with every heuristic; a block pool that is
+    too small makes the alignment rerun with the dense table and still be right."""
+    import os
+    from poasta_b200 import AffineDijkstra, AffineMinGapCost, aligner
+    hap_fa, reads_fa = synth.config5(n_haps=6, root_len=1500, n_reads=10, read_len=300)
+    g = _check_msa([hap_fa])[0]
+    reads = [s for _, s in synth.parse_fasta(reads_fa)]
+
+    def check(expect_table):
+        for cfg, heur in ((AffinePathAware(), 2), (AffineMinGapCost(), 1), (AffineDijkstra(), 0)):
+            for aln_type, mode in ((AlignmentType.EndsFree, 1), (AlignmentType.Global, 0)):
+                res = align_batch([g], reads, [0] * len(reads), cfg, aln_type)
+                # (the blocked launch sizes its queue arena smaller too: a search that outgrows it is rerun with dense full-size
+                # arenas, which is what the wide-open Dijkstra searches do - the layout is asserted where no rerun can happen)
+                if heur == 2 and mode == 1:
+                    assert aligner.last_search_table() == expect_table
+                for q, r in zip(reads, res):
+                    st, sc, pairs, stats = H.oracle_align(g, q, mode=mode, heuristic=heur)
+                    assert st == 0 and r.score == sc and r.alignment == pairs
+                    assert (r.num_queued, r.num_visited, r.num_pruned) == tuple(stats[:3])
+
+    os.environ["POASTA_BLOCKED_TABLE"] = "1"
+    try:
+        check(2)
+        os.environ["POASTA_BLOCKED_POOL_BLOCKS"] = "64"  # fewer blocks than nodes: every alignment overflows and is rerun dense
+        try:
+            check(1)
+        finally:
+            del os.environ["POASTA_BLOCKED_POOL_BLOCKS"]
+    finally:
+        del os.environ["POASTA_BLOCKED_TABLE"]
+    os.environ["POASTA_BLOCKED_TABLE"] = "0"
+    try:
+        check(1)
+    finally:
+        del os.environ["POASTA_BLOCKED_TABLE"]

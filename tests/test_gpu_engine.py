@@ -166,6 +166,8 @@ def test_config5_full_size_graph_reads_sample():
     rows = synth.parse_fasta(g.to_fasta())
     assert all(r.replace(b"-", b"") == s for (_, r), (_, s) in zip(rows, synth.parse_fasta(hap_fa)))
     res = align_batch([g], reads, [0] * len(reads), AffinePathAware(), AlignmentType.EndsFree)
+    from poasta_b200 import aligner
+    assert aligner.last_search_table() == 2, "a 25,000 x 2,000 table per read must run as the blocked table"
     secs, cells, osc = H.oracle_align_many(g, reads, os.cpu_count() or 4, mode=1, heuristic=2, want_scores=True)
     assert [r.score for r in res] == list(osc)
     for q, r in list(zip(reads, res))[:20]:
