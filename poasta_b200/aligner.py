@@ -65,6 +65,11 @@ class AstarResult:
 
 TIEBREAK_EXACT, TIEBREAK_DP = 0, 1
 
+# numpy view of `poasta_result` (_lib.Result)
+_RESULT_DTYPE = np.dtype([("score", "<u4"), ("n_pairs", "<u4"), ("rpos", "<u8"), ("qpos", "<u8"), ("capacity", "<u4"), ("status", "<i4"),
+                          ("num_cells", "<u8"), ("num_queued", "<u8"), ("num_visited", "<u8"), ("num_pruned", "<u8")])
+assert _RESULT_DTYPE.itemsize == C.sizeof(_lib.Result)
+
 
 def _params(config, aln_type, tiebreak=TIEBREAK_EXACT):
     c = config.costs
@@ -85,27 +90,35 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
     qptr = (C.c_char_p * n)(*qs)
     qlens = (C.c_uint32 * n)(*[len(q) for q in qs])
     goq = (C.c_uint32 * n)(*graph_of_query)
-    results = (_lib.Result * n)()
-    bufs = []
-    u32p = C.POINTER(C.c_uint32)
-    for i in range(n):
-        cap = views[graph_of_query[i]].n_nodes + len(qs[i]) + 2
-        r = np.empty(cap, np.uint32)
-        q = np.empty(cap, np.uint32)
-        bufs.append((r, q))
-        results[i].rpos = r.ctypes.data_as(u32p)
-        results[i].qpos = q.ctypes.data_as(u32p)
-        results[i].capacity = cap
+    # one staging area for all alignments (capacity V + Q + 2 pairs each, as the header asks) and the result records filled
+    # as one numpy array: per-problem Python work would dominate batches of short reads (config 5: 20,000 reads per call)
+    qlens_np = np.fromiter((len(q) for q in qs), np.uint64, n)
+    goq_np = np.asarray(graph_of_query, np.int64)
+    nn = np.fromiter((v.n_nodes for v in views), np.uint64, len(graphs))
+    caps = (nn[goq_np] + qlens_np + 2) if n else np.zeros(0, np.uint64)
+    offs = np.zeros(n + 1, np.uint64)
+    np.cumsum(caps, out=offs[1:])
+    rbuf = np.empty(max(1, int(offs[-1])), np.uint32)
+    qbuf = np.empty(max(1, int(offs[-1])), np.uint32)
+    rs = np.zeros(n, _RESULT_DTYPE)
+    rs["rpos"] = rbuf.ctypes.data + offs[:-1] * 4
+    rs["qpos"] = qbuf.ctypes.data + offs[:-1] * 4
+    rs["capacity"] = caps
+    results = rs.ctypes.data_as(C.POINTER(_lib.Result))
     prm = _params(config, aln_type, tiebreak)
     check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
+    bad = np.flatnonzero(rs["status"])
+    if len(bad):
+        check(int(rs["status"][bad[0]]), f"alignment {int(bad[0])}")
     out = []
+    scores, npairs = rs["score"].tolist(), rs["n_pairs"].tolist()
+    nq, nv, npr, nc = rs["num_queued"].tolist(), rs["num_visited"].tolist(), rs["num_pruned"].tolist(), rs["num_cells"].tolist()
+    starts = offs[:-1].tolist()
     for i in range(n):
-        check(results[i].status, f"alignment {i}")
-        k = results[i].n_pairs
-        r, q = bufs[i][0][:k].copy(), bufs[i][1][:k].copy()
-        aln = [AlignedPair(None if a == NONE else int(a), None if b == NONE else int(b)) for a, b in zip(r, q)]
-        out.append(AstarResult(int(results[i].score), aln, int(results[i].num_queued), int(results[i].num_visited),
-                               int(results[i].num_pruned), int(results[i].num_cells), r, q))
+        a, k = starts[i], npairs[i]
+        r, q = rbuf[a:a + k].copy(), qbuf[a:a + k].copy()
+        aln = [AlignedPair(None if x == NONE else x, None if y == NONE else y) for x, y in zip(r.tolist(), q.tolist())]
+        out.append(AstarResult(scores[i], aln, nq[i], nv[i], npr[i], nc[i], r, q))
     return out
 
 
