@@ -259,7 +259,8 @@ def main():
         haps, _ = config5_inputs(args, 0, 0)
         graph = build_config5_graph(haps, device=local)
         batches = [config5_inputs(args, F, step_family_range(k, rank, world, F)[0])[1] for k in range(args.steps)]
-        warm_batches = [config5_inputs(args, max(64, F // 8), step_family_range(args.steps + w, rank, world, F)[0])[1] for w in range(n_warm_batches)]
+        # (a step takes well under a second: full-size warm-up batches, so that every buffer has its final size before the timed steps)
+        warm_batches = [config5_inputs(args, F, step_family_range(args.steps + w, rank, world, F)[0])[1] for w in range(n_warm_batches)]
         view = graph.view()
         real_nodes = graph.node_count()
 

@@ -7,6 +7,10 @@
 ``align`` runs on the GPU (device 0 unless given); there is no CPU path.
 """
 import ctypes as C
+import os
+import sys
+import threading
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -65,6 +69,8 @@ class AstarResult:
 
 TIEBREAK_EXACT, TIEBREAK_DP = 0, 1
 
+_staging = threading.local()  # align_batch's pair staging buffers
+
 # numpy view of `poasta_result` (_lib.Result)
 _RESULT_DTYPE = np.dtype([("score", "<u4"), ("n_pairs", "<u4"), ("rpos", "<u8"), ("qpos", "<u8"), ("capacity", "<u4"), ("status", "<i4"),
                           ("num_cells", "<u8"), ("num_queued", "<u8"), ("num_visited", "<u8"), ("num_pruned", "<u8")])
@@ -80,6 +86,7 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
                 tiebreak=TIEBREAK_EXACT):
     """``poasta_align_batch``: independent (graph, query) problems in one device batch. Returns AstarResult list."""
     lib = _lib.load()
+    t_start = time.perf_counter()
     n = len(queries)
     views = (_lib.GraphView * len(graphs))()
     for i, g in enumerate(graphs):
@@ -98,15 +105,22 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
     caps = (nn[goq_np] + qlens_np + 2) if n else np.zeros(0, np.uint64)
     offs = np.zeros(n + 1, np.uint64)
     np.cumsum(caps, out=offs[1:])
-    rbuf = np.empty(max(1, int(offs[-1])), np.uint32)
-    qbuf = np.empty(max(1, int(offs[-1])), np.uint32)
+    # the staging area is kept across calls (grow-only, per thread): a fresh multi-GB allocation would be page-faulted in anew by
+    # every call, and the results below are copied out of it anyway
+    need = max(1, int(offs[-1]))
+    st = getattr(_staging, "bufs", None)
+    if st is None or len(st[0]) < need:
+        st = _staging.bufs = (np.empty(need + need // 8, np.uint32), np.empty(need + need // 8, np.uint32))
+    rbuf, qbuf = st
     rs = np.zeros(n, _RESULT_DTYPE)
     rs["rpos"] = rbuf.ctypes.data + offs[:-1] * 4
     rs["qpos"] = qbuf.ctypes.data + offs[:-1] * 4
     rs["capacity"] = caps
     results = rs.ctypes.data_as(C.POINTER(_lib.Result))
     prm = _params(config, aln_type, tiebreak)
+    t_call = time.perf_counter()
     check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
+    t_done = time.perf_counter()
     bad = np.flatnonzero(rs["status"])
     if len(bad):
         check(int(rs["status"][bad[0]]), f"alignment {int(bad[0])}")
@@ -119,6 +133,9 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
         r, q = rbuf[a:a + k].copy(), qbuf[a:a + k].copy()
         aln = [AlignedPair(None if x == NONE else x, None if y == NONE else y) for x, y in zip(r.tolist(), q.tolist())]
         out.append(AstarResult(scores[i], aln, nq[i], nv[i], npr[i], nc[i], r, q))
+    if os.environ.get("POASTA_TIMING"):
+        sys.stderr.write(f"poasta_b200 align_batch (python): set-up {t_call - t_start:.3f} s, C call {t_done - t_call:.3f} s, "
+                         f"results {time.perf_counter() - t_done:.3f} s for {n} problems\n")
     return out
 
 
