@@ -266,7 +266,7 @@ def main():
 
         def step(batch):
             t0 = time.perf_counter()
-            res = align_batch([view], batch, [0] * len(batch), AffinePathAware(), AlignmentType.EndsFree, device=local, tiebreak=TIEBREAK_EXACT)
+            res = align_batch([graph], batch, [0] * len(batch), AffinePathAware(), AlignmentType.EndsFree, device=local, tiebreak=TIEBREAK_EXACT)
             wall = time.perf_counter() - t0
             kms, launches, _ = aligner.last_batch_stats()
             sms = aligner.last_batch_search_ms()

@@ -84,6 +84,15 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
                        const uint8_t *const *queries, const uint32_t *qlens,
                        const uint32_t *graph_of_query, uint32_t n_queries,
                        const poasta_params *params, poasta_result *results);
+/* The same for graphs held as handles (poasta_graph, below): what the search and the DP kernels derive from a graph - CSR view,
+ * superbubble / distance / sampled-path index (bubbles/index.rs:51-156, aligner/path_index.rs), node records, rank-ordered layout -
+ * is kept in the handle until the graph changes, so batch after batch against the same graphs (reads against a fixed graph,
+ * bin/poasta.rs `align -g`) does not rebuild it. Replaces PoastaAligner::align(&graph, seq), aligner/mod.rs:114-145. */
+struct poasta_graph;
+int poasta_align_batch_graphs(int device, struct poasta_graph *const *graphs, uint32_t n_graphs,
+                              const uint8_t *const *queries, const uint32_t *qlens,
+                              const uint32_t *graph_of_query, uint32_t n_queries,
+                              const poasta_params *params, poasta_result *results);
 /* Threading: any host thread may call; calls that name the same `device` are serialised inside the library for their
  * whole duration (they share that device's streams and buffers), calls on different devices run concurrently.
  * 0 <= device < 16. */

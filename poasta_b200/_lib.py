@@ -38,7 +38,7 @@ class Result(C.Structure):
 
 # every symbol include/poasta_b200.h declares
 EXPORTS = [
-    "poasta_align_batch", "poasta_last_batch_stats", "poasta_last_dp_kernel", "poasta_last_msa_path", "poasta_last_search_table", "poasta_last_batch_fill_ms", "poasta_last_batch_io", "poasta_last_batch_search_counts", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
+    "poasta_align_batch", "poasta_align_batch_graphs", "poasta_last_batch_stats", "poasta_last_dp_kernel", "poasta_last_msa_path", "poasta_last_search_table", "poasta_last_batch_fill_ms", "poasta_last_batch_io", "poasta_last_batch_search_counts", "poasta_last_batch_search_ms", "poasta_last_batch_device_ms", "poasta_measure_int_peak",
     "poasta_graph_new", "poasta_graph_free", "poasta_graph_free_many", "poasta_graph_node_count",
     "poasta_graph_node_count_with_start_and_end", "poasta_graph_edge_count",
     "poasta_graph_num_sequences", "poasta_graph_add_alignment", "poasta_graph_get_view",
@@ -83,6 +83,8 @@ def load():
     lib.poasta_version.restype = C.c_char_p
     lib.poasta_align_batch.argtypes = [C.c_int, C.POINTER(GraphView), C.c_uint32, C.POINTER(C.c_char_p),
                                        u32p, u32p, C.c_uint32, C.POINTER(Params), C.POINTER(Result)]
+    lib.poasta_align_batch_graphs.argtypes = [C.c_int, C.POINTER(vp), C.c_uint32, C.POINTER(C.c_char_p),
+                                              u32p, u32p, C.c_uint32, C.POINTER(Params), C.POINTER(Result)]
     lib.poasta_last_batch_stats.argtypes = [C.POINTER(C.c_double), u32p, C.POINTER(C.c_uint64)]
     lib.poasta_last_batch_search_ms.argtypes = [C.POINTER(C.c_double)]
     lib.poasta_last_batch_io.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]

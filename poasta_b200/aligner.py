@@ -88,6 +88,9 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
     lib = _lib.load()
     t_start = time.perf_counter()
     n = len(queries)
+    # POAGraph objects go in as handles (the library keeps what it derives from a graph until the graph changes); plain views
+    # (poasta_graph_view structs, e.g. hand-made test graphs) through the view entry point
+    by_handle = len(graphs) > 0 and all(isinstance(g, POAGraph) for g in graphs)
     views = (_lib.GraphView * len(graphs))()
     for i, g in enumerate(graphs):
         views[i] = g.view() if isinstance(g, POAGraph) else g
@@ -119,7 +122,12 @@ def align_batch(graphs, queries, graph_of_query=None, config=AffineMinGapCost(),
     results = rs.ctypes.data_as(C.POINTER(_lib.Result))
     prm = _params(config, aln_type, tiebreak)
     t_call = time.perf_counter()
-    check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
+    if by_handle:
+        handles = (C.c_void_p * len(graphs))(*[g._h if isinstance(g._h, int) else g._h.value for g in graphs])
+        check(lib.poasta_align_batch_graphs(device, handles, len(graphs), qptr, qlens, goq, n, C.byref(prm), results),
+              "poasta_align_batch_graphs")
+    else:
+        check(lib.poasta_align_batch(device, views, len(graphs), qptr, qlens, goq, n, C.byref(prm), results), "poasta_align_batch")
     t_done = time.perf_counter()
     bad = np.flatnonzero(rs["status"])
     if len(bad):

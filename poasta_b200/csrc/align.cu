@@ -1227,22 +1227,9 @@ struct HostPool {
 
 extern "C" {
 
-int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_graphs, const uint8_t *const *queries,
-                       const uint32_t *qlens, const uint32_t *graph_of_query, uint32_t n_queries, const poasta_params *params,
-                       poasta_result *results) {
-    if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
-    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
-    tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
-    tl_lane_max_ms = -1;
-    tl_search_stats.clear();
-    std::vector<Problem> probs(n_queries);
-    for (uint32_t i = 0; i < n_queries; ++i) {
-        const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
-        if (gi >= n_graphs) return POASTA_ERR_INVALID_ARG;
-        probs[i] = {&graphs[gi], gi, queries[i], qlens[i], nullptr, nullptr, nullptr};
-    }
-    return align_problems(device, probs, *params,
+// shared tail of the two align-batch entry points: run the problems, fill the caller's result records
+static int align_batch_results(int device, const std::vector<Problem> &probs, const poasta_params &params, poasta_result *results) {
+    return align_problems(device, probs, params,
                           [&](size_t i, uint32_t score, int32_t status, const uint32_t *r, const uint32_t *q, uint32_t np) {
                               poasta_result &out = results[i];
                               out.score = score;
@@ -1262,6 +1249,62 @@ int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_g
                                   memcpy(out.qpos, q, (size_t)np * 4);
                               }
                           });
+}
+
+int poasta_align_batch(int device, const poasta_graph_view *graphs, uint32_t n_graphs, const uint8_t *const *queries,
+                       const uint32_t *qlens, const uint32_t *graph_of_query, uint32_t n_queries, const poasta_params *params,
+                       poasta_result *results) {
+    if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
+    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
+    tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_lane_max_ms = -1;
+    tl_search_stats.clear();
+    std::vector<Problem> probs(n_queries);
+    for (uint32_t i = 0; i < n_queries; ++i) {
+        const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
+        if (gi >= n_graphs) return POASTA_ERR_INVALID_ARG;
+        probs[i] = {&graphs[gi], gi, queries[i], qlens[i], nullptr, nullptr, nullptr};
+    }
+    return align_batch_results(device, probs, *params, results);
+}
+
+int poasta_align_batch_graphs(int device, poasta_graph *const *graphs, uint32_t n_graphs, const uint8_t *const *queries,
+                              const uint32_t *qlens, const uint32_t *graph_of_query, uint32_t n_queries, const poasta_params *params,
+                              poasta_result *results) {
+    if (!graphs || !queries || !qlens || !params || !results) return POASTA_ERR_INVALID_ARG;
+    if (device < 0 || device >= MAX_DEVICES) return POASTA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> call_lock(device_call_mutex(device));
+    tl_kernel_ms = 0, tl_search_ms = 0, tl_launches = 0, tl_cells = 0, tl_h2d = 0, tl_d2h = 0;
+    tl_lane_max_ms = -1;
+    tl_search_stats.clear();
+    // the handles keep what is derived from a graph (CSR view, bubble / distance / path index, node records, rank-ordered layout)
+    // until the graph changes, so repeated batches against the same graphs do not rebuild it (the reference rebuilds its index for
+    // every single alignment, aligner/config.rs:128)
+    const bool need_index = params->tiebreak == 0, need_pack = params->mode == 0;
+    std::vector<poasta_graph_view> views(n_graphs);
+    std::vector<uint8_t> used(n_graphs, 0);
+    for (uint32_t i = 0; i < n_queries; ++i) {
+        const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
+        if (gi >= n_graphs || !graphs[gi]) return POASTA_ERR_INVALID_ARG;
+        used[gi] = 1;
+    }
+    for (uint32_t g = 0; g < n_graphs; ++g) {
+        if (!used[g]) continue;
+        views[g] = graphs[g]->flat_view();
+        if (views[g].n_nodes <= 2) continue;  // empty graph: the shortcut of aligner/mod.rs:124-142 needs nothing derived
+        if (need_index) graphs[g]->search_index(params->heuristic == 2);
+        if (need_pack) graphs[g]->packed_graph();
+    }
+    std::vector<Problem> probs(n_queries);
+    for (uint32_t i = 0; i < n_queries; ++i) {
+        const uint32_t gi = graph_of_query ? graph_of_query[i] : i;
+        poasta_graph *h = graphs[gi];
+        const bool derived = views[gi].n_nodes > 2;
+        probs[i] = {&views[gi], gi, queries[i], qlens[i], need_index && derived ? &h->sidx : nullptr, need_pack && derived ? &h->packed : nullptr,
+                    need_index && derived ? &h->node_recs : nullptr};
+    }
+    return align_batch_results(device, probs, *params, results);
 }
 
 int poasta_last_batch_stats(double *kernel_ms, uint32_t *n_launches, uint64_t *cells) {
