@@ -31,7 +31,13 @@ def test_no_cpu_fallback_without_device():
     g = POAGraph()
     g.add_alignment_with_weights("s", b"ACGT", None)
     with pytest.raises(CudaError):
-        PoastaAligner().align(g, b"ACGT")
+        PoastaAligner().align(g, b"ACGT")  # graphs as handles: poasta_align_batch_graphs
+    from poasta_b200 import TIEBREAK_DP, align_batch, msa_batch
+    with pytest.raises(CudaError):
+        align_batch([g.view()], [b"ACGT"], [0])  # graphs as CSR views: poasta_align_batch
+    for tiebreak in (0, TIEBREAK_DP):  # the engine and the device-resident DP rounds
+        with pytest.raises(CudaError):
+            msa_batch([b">a\nACGT\n>b\nACGA\n"], tiebreak=tiebreak)
 
 
 def test_product_does_not_reference_oracle():
