@@ -70,16 +70,25 @@ inline bool upload(const POAGraph &g, Family *f, uint8_t *chunk_arena) {
 inline bool download(Family *f, uint8_t *chunk_arena, POAGraph &g, const std::vector<std::string> &names) {
     const Store s(f, chunk_arena);
     const size_t old_n = g.sequences.size();
+    // every list of the graph becomes a slice of one of two pools (PoolList, poa_graph.hpp): two allocations per graph instead of
+    // one per list. The pools are sized first and not touched again, so the slices stay valid; lists the graph already had are
+    // re-pointed without being read.
+    g.al_pool.resize(f->n_als);
+    g.id_pool.resize(f->n_sids);
+    uint32_t *al_pool = g.al_pool.data();
+    uint64_t *id_pool = g.id_pool.data();
+    size_t al_used = 0, id_used = 0;
     g.nodes.resize(f->n_nodes);
     for (uint32_t n = 0; n < f->n_nodes; ++n) {
         POAGraph::Node &nd = g.nodes[n];
         nd.symbol = s.sym[n];
         nd.head[0] = s.head_out[n], nd.head[1] = s.head_in[n];
-        nd.aligned_nodes.clear();
-        size_t n_al = 0;  // one exact allocation per list (a finished graph holds thousands of these small vectors)
-        for (uint32_t k = s.al_head[n]; k != NIL; k = s.al_next[k]) ++n_al;
-        nd.aligned_nodes.reserve(n_al);
-        for (uint32_t k = s.al_head[n]; k != NIL; k = s.al_next[k]) nd.aligned_nodes.push_back(s.al_node[k]);
+        const size_t al0 = al_used;
+        for (uint32_t k = s.al_head[n]; k != NIL; k = s.al_next[k]) {
+            if (al_used >= g.al_pool.size()) return false;  // corrupt arena
+            al_pool[al_used++] = s.al_node[k];
+        }
+        nd.aligned_nodes.set_pool_filled(al_pool + al0, (uint32_t)(al_used - al0));
     }
     g.edges.resize(f->n_edge_slots);
     for (uint32_t e = 0; e < f->n_edge_slots; ++e) {
@@ -88,11 +97,12 @@ inline bool download(Family *f, uint8_t *chunk_arena, POAGraph &g, const std::ve
         ed.next[0] = s.e_next_out[e], ed.next[1] = s.e_next_in[e];
         ed.vacant = s.e_src[e] == NIL;
         ed.weight = s.e_weight[e];
-        ed.sequence_ids.clear();
-        size_t n_id = 0;
-        for (uint32_t k = s.e_sid_head[e]; k != NIL; k = s.sid_next[k]) ++n_id;
-        ed.sequence_ids.reserve(n_id);
-        for (uint32_t k = s.e_sid_head[e]; k != NIL; k = s.sid_next[k]) ed.sequence_ids.push_back(s.sid_val[k]);
+        const size_t id0 = id_used;
+        for (uint32_t k = s.e_sid_head[e]; k != NIL; k = s.sid_next[k]) {
+            if (id_used >= g.id_pool.size()) return false;
+            id_pool[id_used++] = s.sid_val[k];
+        }
+        ed.sequence_ids.set_pool_filled(id_pool + id0, (uint32_t)(id_used - id0));
     }
     g.free_edge = f->free_edge;
     g.live_edges = f->live_edges;

@@ -16,6 +16,9 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -32,24 +35,115 @@ struct AlignedPair {
     uint32_t qpos;
 };
 
+// A small list whose storage is either its own heap block or a slice of a pool owned by the graph. The bulk loader
+// (dev_graph_host.hpp: download of a finished build) points every list of a graph into two pools: a 20 x 1 kb graph holds
+// ~3,000 of these lists, and one allocation per list made both the conversion and the destruction of a batch's 6,000 graphs
+// allocation-bound (0.4 ms per graph). A list that grows past its slice, and every copy, owns its storage.
+template <typename T>
+class PoolList {
+    T *p_ = nullptr;
+    uint32_t n_ = 0, cap_ = 0;
+    bool owned_ = false;
+
+    void release() {
+        if (owned_) free(p_);
+        p_ = nullptr;
+        n_ = cap_ = 0;
+        owned_ = false;
+    }
+    void assign(const T *first, size_t n) {  // [first, first + n) never lies inside this list's own storage
+        release();
+        if (n) {
+            p_ = static_cast<T *>(malloc(n * sizeof(T)));
+            memcpy(p_, first, n * sizeof(T));
+            n_ = cap_ = (uint32_t)n;
+            owned_ = true;
+        }
+    }
+
+  public:
+    PoolList() = default;
+    PoolList(std::initializer_list<T> il) { assign(il.begin(), il.size()); }
+    PoolList(const std::vector<T> &v) { assign(v.data(), v.size()); }
+    PoolList(const PoolList &o) { assign(o.p_, o.n_); }
+    PoolList(PoolList &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_), owned_(o.owned_) {
+        o.p_ = nullptr;
+        o.n_ = o.cap_ = 0;
+        o.owned_ = false;
+    }
+    PoolList &operator=(const PoolList &o) {
+        if (this != &o) assign(o.p_, o.n_);
+        return *this;
+    }
+    PoolList &operator=(PoolList &&o) noexcept {
+        if (this != &o) {
+            release();
+            p_ = o.p_, n_ = o.n_, cap_ = o.cap_, owned_ = o.owned_;
+            o.p_ = nullptr;
+            o.n_ = o.cap_ = 0;
+            o.owned_ = false;
+        }
+        return *this;
+    }
+    PoolList &operator=(const std::vector<T> &v) {
+        assign(v.data(), v.size());
+        return *this;
+    }
+    ~PoolList() { release(); }
+
+    // empty list over `cap` elements of a pool the owner of this list keeps alive (and does not reallocate) while the list lives
+    void set_pool_slice(T *p, uint32_t cap) {
+        release();
+        p_ = p, cap_ = cap;
+    }
+    // the same with the slice already filled
+    void set_pool_filled(T *p, uint32_t n) {
+        release();
+        p_ = p, n_ = cap_ = n;
+    }
+    void clear() { n_ = 0; }
+    void push_back(const T &v) {
+        if (n_ == cap_) {
+            const uint32_t nc = cap_ < 4 ? 4 : cap_ * 2;
+            T *np = static_cast<T *>(malloc((size_t)nc * sizeof(T)));
+            if (n_) memcpy(np, p_, (size_t)n_ * sizeof(T));
+            if (owned_) free(p_);
+            p_ = np, cap_ = nc, owned_ = true;
+        }
+        p_[n_++] = v;
+    }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    bool operator==(const std::vector<T> &v) const { return v.size() == n_ && (n_ == 0 || memcmp(v.data(), p_, (size_t)n_ * sizeof(T)) == 0); }
+    bool operator!=(const std::vector<T> &v) const { return !(*this == v); }
+};
+template <typename T> bool operator==(const std::vector<T> &v, const PoolList<T> &l) { return l == v; }
+template <typename T> bool operator!=(const std::vector<T> &v, const PoolList<T> &l) { return !(l == v); }
+
 struct POAGraph {
     struct Node {
         uint8_t symbol;
         uint32_t head[2];  // head[0] = first outgoing edge, head[1] = first incoming edge
-        std::vector<uint32_t> aligned_nodes;
+        PoolList<uint32_t> aligned_nodes;
     };
     struct Edge {
         uint32_t node[2];  // source, target (NIL,NIL when the slot is vacant)
         uint32_t next[2];  // next edge in source's out list / target's in list
         bool vacant;
         uint64_t weight;
-        std::vector<uint64_t> sequence_ids;
+        PoolList<uint64_t> sequence_ids;
     };
     struct Sequence {
         std::string name;
         uint32_t start_node;
     };
 
+    // pools behind the lists of a bulk-loaded graph; declared before the lists so that they outlive them
+    std::vector<uint32_t> al_pool;
+    std::vector<uint64_t> id_pool;
     std::vector<Node> nodes;
     std::vector<Edge> edges;
     uint32_t free_edge = NIL;
@@ -227,7 +321,7 @@ struct POAGraph {
                     if (curr == NIL) {
                         uint32_t nn = add_node(qsymbol);
                         curr = nn;
-                        std::vector<uint32_t> others = nodes[r].aligned_nodes;
+                        const std::vector<uint32_t> others(nodes[r].aligned_nodes.begin(), nodes[r].aligned_nodes.end());
                         for (uint32_t other : others) {
                             nodes[other].aligned_nodes.push_back(nn);
                             nodes[nn].aligned_nodes.push_back(other);
