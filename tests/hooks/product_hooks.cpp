@@ -235,6 +235,77 @@ int host_insert_timing(const char *fasta, size_t fasta_len, int reps, double *us
     return 0;
 }
 
+// Lifetimes of the pool-backed lists of a downloaded graph (PoolList, poa_graph.hpp; dev_graph_host.hpp download): the graph read
+// back from an arena must serialise like the one it was written from; lists that grow past their pool slice, copies, assignments,
+// moves, a second download into a graph that already has lists, and continuing the build on the host must all leave graphs that
+// serialise like their std-path twins. 0 = all equal. (Run under ASan when changing PoolList.)
+int poollist_lifetime_check(const uint8_t *graph_in, size_t graph_in_len, char *msg, size_t msg_cap) {
+    POAGraph g;
+    if (!graph_from_poasta(graph_in, graph_in_len, g)) FAIL("bad graph_in");
+    const dg::Occupancy occ = dg::occupancy(g);
+    dg::Family fam;
+    memset(&fam, 0, sizeof fam);
+    fam.cap = dg::Caps{occ.V, occ.E, occ.I + 1, occ.A + 1, occ.N + 1};
+    std::vector<uint8_t> arena(dg::Layout(fam.cap).total);
+    if (!dg::upload(g, &fam, arena.data())) FAIL("upload failed");
+    std::vector<std::string> names;
+    for (auto &sq : g.sequences) names.push_back(sq.name);
+    auto bytes = [](const POAGraph &x) {
+        std::string out;
+        graph_to_poasta(x, out);
+        return out;
+    };
+    const std::string want = bytes(g);
+    auto load = [&](POAGraph &into) {
+        dg::Family F = fam;
+        return dg::download(&F, arena.data(), into, names);
+    };
+    POAGraph h;
+    if (!load(h)) FAIL("download failed");
+    if (bytes(h) != want) FAIL("downloaded graph serialises differently");
+    // grow lists past their slices, on the pool-backed graph and on its std-path twin
+    POAGraph twin = g;
+    for (int i = 0; i < 10; ++i) h.nodes[2].aligned_nodes.push_back(7 + i), twin.nodes[2].aligned_nodes.push_back(7 + i);
+    for (size_t e = 0; e < h.edges.size() && e < 50; ++e)
+        if (!h.edges[e].vacant)
+            for (int i = 0; i < 40; ++i) h.edges[e].sequence_ids.push_back(1000 + i), twin.edges[e].sequence_ids.push_back(1000 + i);
+    if (bytes(h) != bytes(twin)) FAIL("lists grown past their pool slices differ");
+    POAGraph c = h;  // copy: owning lists
+    if (bytes(c) != bytes(twin)) FAIL("copy differs");
+    h = c;           // copy-assignment over pool-backed lists
+    POAGraph m = std::move(c);
+    if (bytes(h) != bytes(twin) || bytes(m) != bytes(twin)) FAIL("assignment / move differs");
+    if (!load(h) || !load(m)) FAIL("second download failed");  // re-points every list of graphs that already had lists
+    if (bytes(h) != want || bytes(m) != want) FAIL("second download differs");
+    // continue the build on the host (new nodes, new edges, ids appended to pool-backed lists, start / end edges recycled)
+    const uint8_t extra[] = "ACGTTGCAACGT";
+    POAGraph t2 = g;
+    if (h.add_alignment_with_weights("x", extra, 12, false, nullptr, 0) != t2.add_alignment_with_weights("x", extra, 12, false, nullptr, 0))
+        FAIL("insert status differs");
+    std::vector<AlignedPair> aln;  // the first sequence of the graph against itself: walk its path
+    std::string seq;
+    for (uint32_t v = g.sequences[0].start_node; v != g.end_node && seq.size() < 400;) {
+        aln.push_back({v, (uint32_t)seq.size()});
+        seq.push_back((char)g.nodes[v].symbol);
+        uint32_t next = NIL;
+        for (uint32_t e = g.nodes[v].head[0]; e != NIL; e = g.edges[e].next[0])
+            if (std::binary_search(g.edges[e].sequence_ids.begin(), g.edges[e].sequence_ids.end(), (uint64_t)0)) next = g.edges[e].node[1];
+        if (next == NIL) break;
+        v = next;
+    }
+    if (h.add_alignment_with_weights("y", (const uint8_t *)seq.data(), seq.size(), true, aln.data(), aln.size()) !=
+        t2.add_alignment_with_weights("y", (const uint8_t *)seq.data(), seq.size(), true, aln.data(), aln.size()))
+        FAIL("insert status differs (aligned)");
+    if (bytes(h) != bytes(t2)) FAIL("graphs differ after continuing the build on the host");
+    std::vector<POAGraph> v;
+    v.push_back(h);
+    v.push_back(std::move(m));
+    v.resize(6);
+    v.erase(v.begin());
+    if (bytes(v[0]) != want) FAIL("moved graph differs");
+    return 0;
+}
+
 // Host build of the product's order-exact search core (poasta_b200/csrc/replay_core.hpp), for CPU-side tests of the
 // logic that runs on the device. TEST HOOK ONLY: the product never executes this path (it has no CPU fallback).
 int replay_host_align(const poasta_graph_view *view, const uint8_t *seq, uint32_t qlen, int x, int o, int e, int mode,

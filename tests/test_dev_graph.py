@@ -50,3 +50,15 @@ def test_full_size_family_and_existing_graph():
 def test_degenerate_records():
     assert _check(b">a\nACGT\n>b\n\n>c\nACGA\n") == (0, "")
     assert _check(b">a\nA\n>b\nC\n>c\nA\n>d\nG\n>e\nT\n>f\nN\n") == (0, "")  # one column of five mutually aligned nodes
+
+
+def test_pool_backed_lists_of_a_downloaded_graph():
+    """PoolList lifetimes (poa_graph.hpp): download, growth past the pool slice, copy / assign / move, second download, continuing
+    the build on the host - every graph must serialise like its std-path twin."""
+    lib = H.oracle()
+    lib.poollist_lifetime_check.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    for fa in (synth.config2_family(4, n_seqs=8, root_len=300, rate=0.08), synth.family(78, 6, 150, 0.25)):
+        rc, data, _, _ = H.oracle_msa(fa, fmt=3)
+        assert rc == 0
+        msg = C.create_string_buffer(512)
+        assert (lib.poollist_lifetime_check(data, len(data), msg, 512), msg.value.decode()) == (0, "")
